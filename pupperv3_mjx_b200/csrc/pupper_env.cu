@@ -1,0 +1,755 @@
+// pupper_env.cu -- env-level kernel (reset / step) and the C ABI declared in include/pupper_env.h.
+// Env level = reference pupperv3_mjx/environment.py:314-543 + rewards.py:9-138 + utils.py:49-69;
+// physics = pupper_kernel.cuh.  No CPU fallback: every entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "pupper_kernel.cuh"
+
+namespace pupper {
+
+__device__ __forceinline__ uint2 qbcast2(uint2 v, int src, unsigned qm, int qbase) {
+  return make_uint2(__shfl_sync(qm, v.x, qbase + src), __shfl_sync(qm, v.y, qbase + src));
+}
+
+// jax.random.choice index from the uniform draw u: searchsorted(cumsum(p), cumsum(p)[-1] * (1 - u))
+__device__ __forceinline__ int choice_from_u(float u, const float *p, int n) {
+  float cum[PUPPER_MAX_LAT];
+  float acc = 0.f;
+  for (int i = 0; i < n; i++) { acc = __fadd_rn(acc, p[i]); cum[i] = acc; }
+  float r = __fmul_rn(acc, __fsub_rn(1.0f, u));
+  int idx = 0;
+  for (int i = 0; i < n; i++) idx += (cum[i] < r) ? 1 : 0;
+  return min(idx, n - 1);
+}
+
+// environment.py:246-272 (evaluated by one lane)
+__device__ __noinline__ void sample_command(const PupperEnvCfg &c, uint2 key, float cmd[3]) {
+  uint2 k1 = split_key(key, 1), k2 = split_key(key, 2), k3 = split_key(key, 3), k4 = split_key(key, 4), k5 = split_key(key, 5);
+  float c0 = uniform(k1, 0, c.lin_vel_x[0], c.lin_vel_x[1]);
+  float c1 = uniform(k2, 0, c.lin_vel_y[0], c.lin_vel_y[1]);
+  float c2 = uniform(k3, 0, c.ang_vel_yaw[0], c.ang_vel_yaw[1]);
+  float zp = uniform(k4, 0, 0.f, 1.f);
+  float thr = c.stand_still_command_threshold;
+  if (zp < c.zero_command_probability) {
+    cmd[0] = uniform(k5, 0, -thr, thr); cmd[1] = uniform(k5, 1, -thr, thr); cmd[2] = uniform(k5, 2, -thr, thr);
+  } else { cmd[0] = c0; cmd[1] = c1; cmd[2] = c2; }
+}
+
+// environment.py:274-298 (evaluated by one lane)
+__device__ __noinline__ void sample_body_orientation(const PupperEnvCfg &c, uint2 key, float out[3]) {
+  uint2 kp = split_key(key, 1), kr = split_key(key, 2);
+  float pitch = __fmul_rn(uniform(kp, 0, -1.f, 1.f), c.maximum_pitch_command);
+  float roll = __fmul_rn(uniform(kr, 0, -1.f, 1.f), c.maximum_roll_command);
+  const float pi = 3.14159274101257324f;
+  float a1 = roll * pi / 360.f, a2 = pitch * pi / 360.f;
+  float s1, c1, s2, c2;
+  sincosf(a1, &s1, &c1);
+  sincosf(a2, &s2, &c2);
+  const float s3 = 0.f, c3 = 1.f;
+  Q4 q = Q4{c1 * c2 * c3 - s1 * s2 * s3, s1 * c2 * c3 + c1 * s2 * s3, c1 * s2 * c3 - s1 * c2 * s3, c1 * c2 * s3 + s1 * s2 * c3};
+  V3 z = rotate(V3{c.desired_world_z_in_body_frame[0], c.desired_world_z_in_body_frame[1], c.desired_world_z_in_body_frame[2]}, q);
+  out[0] = z.x; out[1] = z.y; out[2] = z.z;
+}
+
+struct ObsCtx {
+  float command[3], desired_z[3];
+  float last_act[3];   // this leg's channels
+  float ql[3];
+};
+
+// _get_obs (environment.py:485-543). `rng` is info["rng"] on entry; returns the new info["rng"].
+// Updates the IMU buffer and the observation history in global memory.
+__device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p, int e, int k, unsigned qm, int qbase, uint2 rng,
+                                         const StaleOut &so, const ObsCtx &oc, bool zero_history) {
+  const PupperEnvCfg &c = sh.c;
+  const int stride = p.st.stride;
+  // split(rng, 6): lane 0 -> new rng, lane 1 -> ang key, lane 2 -> gravity key, lane 3 -> imu sample key
+  uint2 kmine = split_key(rng, k == 3 ? 5u : (uint32_t)k);
+  uint2 k_motor = split_key(rng, 3u), k_act = split_key(rng, 4u);
+  uint2 new_rng = qbcast2(kmine, 0, qm, qbase), k_ang = qbcast2(kmine, 1, qm, qbase), k_grav = qbcast2(kmine, 2, qm, qbase);
+  // one draw per lane: lanes 0-2 angular-velocity noise component k, lane 3 the IMU latency draw
+  float uA = uniform(k < 3 ? k_ang : kmine, k < 3 ? (uint32_t)k : 0u, k < 3 ? -1.f : 0.f, 1.f);
+  float uB = uniform(k_grav, (uint32_t)k, -1.f, 1.f);
+  float an_mine = __fmul_rn(uA, c.angular_velocity_noise), gn_mine = __fmul_rn(uB, c.gravity_noise);
+  float an[3], gn[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { an[i] = __shfl_sync(qm, an_mine, qbase + i); gn[i] = __shfl_sync(qm, gn_mine, qbase + i); }
+  int imu_idx = k == 3 ? choice_from_u(uA, c.imu_latency_distribution, c.n_imu_latency) : 0;
+  imu_idx = __shfl_sync(qm, imu_idx, qbase + 3);
+
+  Q4 inv = Q4{1.f, 0.f, 0.f, 0.f};
+  V3 ang = V3{0.f, 0.f, 0.f};
+  if (c.use_imu) { inv = qinv(so.torso_rot); ang = rotate(so.torso_ang, inv); }
+  V3 g = rotate(V3{0.f, 0.f, -1.f}, inv);
+  g = V3{g.x + gn[0], g.y + gn[1], g.z + gn[2]};
+  float gnorm = sqrtf(g.x * g.x + g.y * g.y + g.z * g.z);
+  float imu[6] = {ang.x + an[0], ang.y + an[1], ang.z + an[2], g.x / gnorm, g.y / gnorm, g.z / gnorm};
+
+  // IMU lag buffer (6, L): this lane handles rows k and k+4
+  const int Li = c.n_imu_latency;
+  float lag_imu[2] = {0.f, 0.f};
+#pragma unroll
+  for (int t = 0; t < 2; t++) {
+    int row = k + 4 * t;
+    if (row < 6) {
+      float prev = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; i++) if (i == row) prev = imu[i];
+      float lag = prev;
+      for (int l = 0; l < Li; l++) {
+        float *ptr = p.st.imu_buffer + (size_t)(row * Li + l) * stride + e;
+        float old = zero_history ? (row == 5 ? -1.f : 0.f) : *ptr;
+        *ptr = prev;
+        if (l == imu_idx) lag = prev;
+        prev = old;
+      }
+      lag_imu[t] = lag;
+    }
+  }
+
+  // history roll: slot h <- slot h-1 (each lane moves the entries i = k (mod 4))
+  const int H = c.observation_history;
+  float *obs = p.st.obs + (size_t)e * H * PUPPER_OBS_DIM;
+  for (int h = H - 1; h >= 1; h--)
+    for (int i = k; i < PUPPER_OBS_DIM; i += 4) obs[h * PUPPER_OBS_DIM + i] = zero_history ? 0.f : obs[(h - 1) * PUPPER_OBS_DIM + i];
+  __syncwarp(qm);
+  auto clip100 = [](float x) { return fminf(fmaxf(x, -100.f), 100.f); };
+  // entries 0..11: imu(6), command(3), desired_z(3); this lane writes i = k, k+4, k+8
+  {
+    obs[k] = clip100(lag_imu[0]);
+    int i1 = k + 4;
+    float v1 = i1 < 6 ? lag_imu[1] : (i1 == 6 ? oc.command[0] : oc.command[1]);
+    obs[i1] = clip100(v1);
+    int i2 = k + 8;
+    float v2 = i2 == 8 ? oc.command[2] : (i2 == 9 ? oc.desired_z[0] : (i2 == 10 ? oc.desired_z[1] : oc.desired_z[2]));
+    obs[i2] = clip100(v2);
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int u = 3 * k + j;
+    float mn = __fmul_rn(uniform(k_motor, (uint32_t)u, -1.f, 1.f), c.motor_angle_noise);
+    float ln = __fmul_rn(uniform(k_act, (uint32_t)u, -1.f, 1.f), c.last_action_noise);
+    obs[12 + u] = clip100(oc.ql[j] - c.default_pose[u] + mn);
+    obs[24 + u] = clip100(oc.last_act[j] + ln);
+  }
+  return new_rng;
+}
+
+template <bool RESET, bool DBG>
+__global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
+  __shared__ BlockShared sh;
+  {
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.model);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.m);
+    for (int i = threadIdx.x; i < (int)(sizeof(PupperModelDesc) / 4); i += kBlock) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t *>(p.cfg);
+    dst = reinterpret_cast<uint32_t *>(&sh.c);
+    for (int i = threadIdx.x; i < (int)(sizeof(PupperEnvCfg) / 4); i += kBlock) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, k = threadIdx.x & 3;
+  const int el = threadIdx.x >> 2;
+  const int e = blockIdx.x * kEnvsPerBlock + el;
+  if (e >= p.n_envs) return;
+  const unsigned qm = 0xFu << (lane & 28);
+  const int qbase = lane & 28;
+  const PupperModelDesc &m = sh.m;
+  const PupperEnvCfg &c = sh.c;
+  EnvShared &es = sh.env[el];
+  const int stride = p.st.stride;
+
+  // ---- stage the per-env DR leaves (or the nominal values) in shared memory --------------------------
+  for (int i = k; i < 58; i += 4) {
+    float v;
+    if (p.has_dr) {
+      const int ds = p.dr.stride;
+      if (i < 13) v = p.dr.body_mass[(size_t)i * ds + e];
+      else if (i < 52) v = p.dr.body_inertia[(size_t)(i - 13) * ds + e];
+      else if (i < 55) v = p.dr.base_ipos[(size_t)(i - 52) * ds + e];
+      else if (i == 55) v = p.dr.friction[e];
+      else if (i == 56) v = p.dr.kp[e];
+      else v = p.dr.kd[e];
+    } else {
+      if (i < 13) v = m.body_mass[1 + i];
+      else if (i < 52) v = m.body_inertia[1 + (i - 13) / 3][(i - 13) % 3];
+      else if (i < 55) v = m.body_ipos[1][i - 52];
+      else if (i == 55) v = -1.f;
+      else if (i == 56) v = m.act_gain[0];
+      else v = -m.act_bias2[0];
+    }
+    if (i < 13) es.mass[i] = v;
+    else if (i < 52) es.inertia[i - 13] = v;
+    else if (i < 55) es.ipos[i - 52] = v;
+    else if (i == 55) es.friction = v;
+    else if (i == 56) es.kp = v;
+    else es.kd = v;
+  }
+  __syncwarp(qm);
+
+  LaneState L;
+  StaleOut so;
+  DbgOut dbg;
+  ObsCtx oc;
+  float ab[6], al[3];
+  uint2 rng;
+  const int H = c.observation_history;
+
+  if (RESET) {
+    // ---- reset (environment.py:314-346), replicated over the quad where it is per-env ------------------
+    uint2 key = make_uint2(p.keys[2 * e], p.keys[2 * e + 1]);
+    uint2 k_rng = split_key(key, 0), k_cmd = split_key(key, 1), k_ori = split_key(key, 2), k_pos = split_key(key, 3);
+    uint2 kp = split_key(k_pos, 1), ky = split_key(k_pos, 2);
+#pragma unroll
+    for (int i = 0; i < 7; i++) L.qb[i] = c.init_q[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) L.qb[i] = uniform(kp, (uint32_t)i, c.start_pos_min[i], c.start_pos_max[i]);
+    {
+      float yaw = uniform(ky, 0u, -3.14159274101257324f, 3.14159274101257324f);
+      float s, cs;
+      sincosf(yaw / 2.f, &s, &cs);
+      L.qb[3] = cs; L.qb[4] = 0.f; L.qb[5] = 0.f; L.qb[6] = s;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { L.ql[j] = c.init_q[7 + 3 * k + j]; L.vl[j] = 0.f; L.wl[j] = 0.f; L.ctrl[j] = 0.f; }
+#pragma unroll
+    for (int d = 0; d < 6; d++) { L.vb[d] = 0.f; L.wb[d] = 0.f; }
+    forward<DBG>(sh, es, L, k, qm, qbase, ab, al, true, so, &dbg);  // pipeline_init = make_data + forward
+#pragma unroll
+    for (int d = 0; d < 6; d++) L.wb[d] = ab[d];
+#pragma unroll
+    for (int j = 0; j < 3; j++) L.wl[j] = al[j];
+    float cmd[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
+    if (k == 0) { sample_command(c, k_cmd, cmd); sample_body_orientation(c, k_ori, dz); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { oc.command[i] = __shfl_sync(qm, cmd[i], qbase); oc.desired_z[i] = __shfl_sync(qm, dz[i], qbase); }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { oc.last_act[j] = 0.f; oc.ql[j] = L.ql[j]; }
+    rng = get_obs(sh, p, e, k, qm, qbase, k_rng, so, oc, true);
+    // info / state
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int u = 3 * k + j;
+      p.st.last_act[(size_t)u * stride + e] = 0.f;
+      p.st.last_vel[(size_t)u * stride + e] = 0.f;
+      for (int l = 0; l < c.n_latency; l++) p.st.action_buffer[(size_t)(u * c.n_latency + l) * stride + e] = 0.f;
+    }
+    p.st.feet_air_time[(size_t)k * stride + e] = 0.f;
+    if (k == 0) {
+      p.st.last_contact[e] = 0u; p.st.step[e] = 0;
+      p.st.kick[e] = 0.f; p.st.kick[stride + e] = 0.f;
+      p.out.reward[e] = 0.f; p.out.done[e] = 0.f;
+    }
+    for (int i = k; i < PUPPER_NMETRIC; i += 4) p.out.metrics[(size_t)e * PUPPER_NMETRIC + i] = 0.f;
+  } else {
+    // ---- step (environment.py:348-483) ---------------------------------------------------------------------
+    rng = make_uint2(p.st.rng[e], p.st.rng[stride + e]);
+#pragma unroll
+    for (int i = 0; i < 7; i++) L.qb[i] = p.st.qpos[(size_t)i * stride + e];
+#pragma unroll
+    for (int d = 0; d < 6; d++) { L.vb[d] = p.st.qvel[(size_t)d * stride + e]; L.wb[d] = p.st.qacc_warmstart[(size_t)d * stride + e]; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int u = 3 * k + j;
+      L.ql[j] = p.st.qpos[(size_t)(7 + u) * stride + e];
+      L.vl[j] = p.st.qvel[(size_t)(6 + u) * stride + e];
+      L.wl[j] = p.st.qacc_warmstart[(size_t)(6 + u) * stride + e];
+      oc.last_act[j] = p.st.last_act[(size_t)u * stride + e];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { oc.command[i] = p.st.command[(size_t)i * stride + e]; oc.desired_z[i] = p.st.desired_world_z[(size_t)i * stride + e]; }
+  }
+
+  float act[3] = {0.f, 0.f, 0.f};
+  float kick0 = 0.f, kick1 = 0.f;
+  uint2 cmd_rng = make_uint2(0u, 0u);
+  if (!RESET) {
+    // S1 split(rng, 5): lane k computes key k; lane 3 also needs key 4 (latency)
+    uint2 kmine = split_key(rng, (uint32_t)k);
+    uint2 k4 = split_key(rng, 4u);
+    uint2 K0 = qbcast2(kmine, 0, qm, qbase), K1 = qbcast2(kmine, 1, qm, qbase), K2 = qbcast2(kmine, 2, qm, qbase);
+    cmd_rng = K1;
+    // S2/S3 draws, one per lane: kick x, kick y, kick Bernoulli, latency pick
+    // (lane 0: kick x, lane 1: kick y, lane 2: latency pick with key 4, lane 3: Bernoulli with its own key 3)
+    float u = uniform(k < 2 ? K2 : (k == 2 ? k4 : kmine), k == 1 ? 1u : 0u, k < 2 ? -1.f : 0.f, 1.f);
+    float kv = __fmul_rn(u, c.kick_vel);
+    float hit = __shfl_sync(qm, (u < c.kick_probability) ? 1.f : 0.f, qbase + 3);
+    kick0 = __fmul_rn(__shfl_sync(qm, kv, qbase + 0), hit);
+    kick1 = __fmul_rn(__shfl_sync(qm, kv, qbase + 1), hit);
+    int aidx = k == 2 ? choice_from_u(u, c.latency_distribution, c.n_latency) : 0;
+    aidx = __shfl_sync(qm, aidx, qbase + 2);
+    L.vb[0] = kick0 + L.vb[0];
+    L.vb[1] = kick1 + L.vb[1];
+    // action latency buffer (12, L): push front, take column aidx; S4 motor targets
+    const int La = c.n_latency;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int u_ = 3 * k + j;
+      act[j] = p.action[(size_t)e * PUPPER_NU + u_];
+      float prev = act[j], lag = act[j];
+      for (int l = 0; l < La; l++) {
+        float *ptr = p.st.action_buffer + (size_t)(u_ * La + l) * stride + e;
+        float old = *ptr;
+        *ptr = prev;
+        if (l == aidx) lag = prev;
+        prev = old;
+      }
+      float t = c.default_pose[u_] + lag * c.action_scale;
+      L.ctrl[j] = fminf(fmaxf(t, c.joint_lower[u_]), c.joint_upper[u_]);
+    }
+    rng = K0;
+    // S5 physics: n_frames x (forward ; semi-implicit Euler)
+    const float dt = m.timestep;
+    for (int f = 0; f < c.n_frames; f++) {
+      forward<DBG>(sh, es, L, k, qm, qbase, ab, al, f == c.n_frames - 1, so, &dbg);
+#pragma unroll
+      for (int d = 0; d < 6; d++) { L.wb[d] = ab[d]; L.vb[d] = fmaf(ab[d], dt, L.vb[d]); }
+#pragma unroll
+      for (int j = 0; j < 3; j++) { L.wl[j] = al[j]; L.vl[j] = fmaf(al[j], dt, L.vl[j]); L.ql[j] = fmaf(dt, L.vl[j], L.ql[j]); }
+      L.qb[0] = fmaf(dt, L.vb[0], L.qb[0]); L.qb[1] = fmaf(dt, L.vb[1], L.qb[1]); L.qb[2] = fmaf(dt, L.vb[2], L.qb[2]);
+      V3 w = V3{L.vb[3], L.vb[4], L.vb[5]};
+      float nrm = normalize3(w);
+      float sn, cs;
+      sincosf(dt * nrm * 0.5f, &sn, &cs);
+      Q4 qn = qnormalize(qmul(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]}, Q4{cs, w.x * sn, w.y * sn, w.z * sn}));
+      L.qb[3] = qn.w; L.qb[4] = qn.x; L.qb[5] = qn.y; L.qb[6] = qn.z;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) oc.ql[j] = L.ql[j];
+    // S6 observation (reads the not-yet-updated last_act / command / desired_z)
+    rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false);
+  }
+
+  // ---- write back the physics state -------------------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int u = 3 * k + j;
+    p.st.qpos[(size_t)(7 + u) * stride + e] = L.ql[j];
+    p.st.qvel[(size_t)(6 + u) * stride + e] = L.vl[j];
+    p.st.qacc_warmstart[(size_t)(6 + u) * stride + e] = L.wl[j];
+  }
+  for (int i = k; i < 7; i += 4) {
+    float v = 0.f;
+#pragma unroll
+    for (int t = 0; t < 7; t++) if (t == i) v = L.qb[t];
+    p.st.qpos[(size_t)i * stride + e] = v;
+  }
+  for (int i = k; i < 6; i += 4) {
+    float v = 0.f, w = 0.f;
+#pragma unroll
+    for (int t = 0; t < 6; t++) if (t == i) { v = L.vb[t]; w = L.wb[t]; }
+    p.st.qvel[(size_t)i * stride + e] = v;
+    p.st.qacc_warmstart[(size_t)i * stride + e] = w;
+  }
+  if (k == 0) { p.st.rng[e] = rng.x; p.st.rng[stride + e] = rng.y; }
+
+  if (DBG) {
+    if (p.out.dbg_x_pos) {
+      float *xp = p.out.dbg_x_pos + (size_t)e * 39, *xr = p.out.dbg_x_rot + (size_t)e * 52;
+      float *xv = p.out.dbg_xd_vel + (size_t)e * 39, *xa = p.out.dbg_xd_ang + (size_t)e * 39;
+      if (k == 0) {
+        xp[0] = so.torso_pos.x; xp[1] = so.torso_pos.y; xp[2] = so.torso_pos.z;
+        xr[0] = so.torso_rot.w; xr[1] = so.torso_rot.x; xr[2] = so.torso_rot.y; xr[3] = so.torso_rot.z;
+        xv[0] = so.torso_vel.x; xv[1] = so.torso_vel.y; xv[2] = so.torso_vel.z;
+        xa[0] = so.torso_ang.x; xa[1] = so.torso_ang.y; xa[2] = so.torso_ang.z;
+      }
+      for (int j = 0; j < 3; j++) {
+        int b = 1 + 3 * k + j;
+        xp[3 * b] = dbg.pos[j].x; xp[3 * b + 1] = dbg.pos[j].y; xp[3 * b + 2] = dbg.pos[j].z;
+        xr[4 * b] = dbg.rot[j].w; xr[4 * b + 1] = dbg.rot[j].x; xr[4 * b + 2] = dbg.rot[j].y; xr[4 * b + 3] = dbg.rot[j].z;
+        xv[3 * b] = dbg.vel[j].x; xv[3 * b + 1] = dbg.vel[j].y; xv[3 * b + 2] = dbg.vel[j].z;
+        xa[3 * b] = dbg.ang[j].x; xa[3 * b + 1] = dbg.ang[j].y; xa[3 * b + 2] = dbg.ang[j].z;
+      }
+    }
+    if (p.out.dbg_qfrc_actuator) {
+      float *o = p.out.dbg_qfrc_actuator + (size_t)e * 18;
+      for (int j = 0; j < 3; j++) o[6 + 3 * k + j] = so.frc[j];
+      if (k == 0) for (int d = 0; d < 6; d++) o[d] = 0.f;
+    }
+    if (p.out.dbg_qacc) {
+      float *o = p.out.dbg_qacc + (size_t)e * 18;
+      for (int j = 0; j < 3; j++) o[6 + 3 * k + j] = dbg.qacc_l[j];
+      if (k == 0) for (int d = 0; d < 6; d++) o[d] = dbg.qacc_b[d];
+    }
+    if (p.out.dbg_site_xpos) {
+      float *o = p.out.dbg_site_xpos + (size_t)e * 15;
+      o[3 + 3 * k] = so.foot_site.x; o[4 + 3 * k] = so.foot_site.y; o[5 + 3 * k] = so.foot_site.z;
+      if (k == 0) {
+        V3 s = so.torso_pos + rotate(V3{m.site_pos[0][0], m.site_pos[0][1], m.site_pos[0][2]}, so.torso_rot);
+        o[0] = s.x; o[1] = s.y; o[2] = s.z;
+      }
+    }
+    if (p.out.dbg_contact_dist && k == 0) {
+      const int mc = m.max_contact_points;
+      for (int i = 0; i < mc; i++) {
+        bool on = i < es.ncon;
+        p.out.dbg_contact_dist[(size_t)e * mc + i] = on ? es.con[i].dist : 1.0f;
+        int g1 = -1, g2 = -1;
+        if (on) {
+          const ContactSlot &s = es.con[i];
+          g1 = s.s1 >= 0 ? m.sphere_geomid[s.s1] : m.floor_geomid;
+          g2 = s.s2 >= 0 ? m.sphere_geomid[s.s2] : -2;  // -2: a world box (id not tracked)
+        }
+        p.out.dbg_contact_geom[((size_t)e * mc + i) * 2] = g1;
+        p.out.dbg_contact_geom[((size_t)e * mc + i) * 2 + 1] = g2;
+      }
+    }
+  }
+
+  if (RESET) {
+    // persistent info written by reset; fused wrapper state
+#pragma unroll
+    for (int i = 0; i < 3; i++) if (k == i) { p.st.command[(size_t)i * stride + e] = oc.command[i]; p.st.desired_world_z[(size_t)i * stride + e] = oc.desired_z[i]; }
+    if (p.has_ep) {
+      const int es_ = p.ep.stride;
+      __syncwarp(qm);
+      for (int i = k; i < PUPPER_NQ; i += 4) p.ep.first_qpos[(size_t)i * es_ + e] = p.st.qpos[(size_t)i * stride + e];
+      for (int i = k; i < PUPPER_NV; i += 4) {
+        p.ep.first_qvel[(size_t)i * es_ + e] = p.st.qvel[(size_t)i * stride + e];
+        p.ep.first_warmstart[(size_t)i * es_ + e] = p.st.qacc_warmstart[(size_t)i * stride + e];
+      }
+      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i];
+      for (int i = k; i < PUPPER_NMETRIC; i += 4) p.ep.sum_metrics[(size_t)i * es_ + e] = 0.f;
+      if (k == 0) { p.ep.steps[e] = 0; p.ep.truncation[e] = 0.f; p.ep.sum_reward[e] = 0.f; p.ep.length[e] = 0.f; p.ep.episode_done[e] = 0.f; }
+    }
+    return;
+  }
+
+  // ---- S7 foot contacts (own foot) -----------------------------------------------------------------------------
+  const float dtenv = c.dt;
+  const uint32_t last_contact = p.st.last_contact[e];
+  const bool lc = (last_contact >> k) & 1u;
+  const float fz = so.foot_site.z - c.foot_radius;
+  const bool contact = fz < 1e-3f;
+  const bool filt_mm = contact || lc;
+  const bool filt_cm = (fz < 3e-2f) || lc;
+  float air = p.st.feet_air_time[(size_t)k * stride + e];
+  const bool first = (air > 0.f) && filt_mm;
+  air += dtenv;
+
+  // ---- S8 termination ------------------------------------------------------------------------------------------
+  const V3 up = V3{0.f, 0.f, 1.f};
+  const V3 rup = rotate(up, so.torso_rot);
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 3; j++) bad |= (L.ql[j] < c.joint_lower[3 * k + j]) || (L.ql[j] > c.joint_upper[3 * k + j]);
+  bool done = (__ballot_sync(qm, bad) & qm) != 0u;
+  done |= rup.z < c.cos_terminal_body_angle;
+  done |= so.torso_pos.z < c.terminal_body_z;
+  const int step0 = p.st.step[e];
+
+  // ---- S9 rewards (rewards.py) ----------------------------------------------------------------------------------
+  float rw[PUPPER_NREWARD];
+  {
+    const Q4 inv = qinv(so.torso_rot);
+    const V3 lv = rotate(so.torso_vel, inv), av = rotate(so.torso_ang, inv), wz = rotate(up, inv);
+    const float sigma = c.tracking_sigma;
+    float e0 = oc.command[0] - lv.x, e1 = oc.command[1] - lv.y, e2 = oc.command[2] - av.z;
+    rw[PUPPER_R_TRACKING_LIN_VEL] = expf(-(e0 * e0 + e1 * e1) / sigma);
+    rw[PUPPER_R_TRACKING_ANG_VEL] = expf(-(e2 * e2) / sigma);
+    float d0 = wz.x - oc.desired_z[0], d1 = wz.y - oc.desired_z[1], d2 = wz.z - oc.desired_z[2];
+    rw[PUPPER_R_TRACKING_ORIENTATION] = expf(-(d0 * d0 + d1 * d1 + d2 * d2) / sigma);
+    rw[PUPPER_R_LIN_VEL_Z] = so.torso_vel.z * so.torso_vel.z;
+    rw[PUPPER_R_ANG_VEL_XY] = so.torso_ang.x * so.torso_ang.x + so.torso_ang.y * so.torso_ang.y;
+    rw[PUPPER_R_ORIENTATION] = rup.x * rup.x + rup.y * rup.y;
+    float tq = 0.f, ja = 0.f, mw = 0.f, ar = 0.f, ss = 0.f, sv = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int u = 3 * k + j;
+      float lvj = p.st.last_vel[(size_t)u * stride + e];
+      tq = fmaf(so.frc[j], so.frc[j], tq);
+      float a = (L.vl[j] - lvj) / c.env_dt;
+      ja = fmaf(a, a, ja);
+      mw += fabsf(so.frc[j] * L.vl[j]);
+      float da = act[j] - oc.last_act[j];
+      ar = fmaf(da, da, ar);
+      ss += fabsf(L.ql[j] - c.default_pose[u]);
+      sv += fabsf(L.vl[j]);
+    }
+    float abd = L.ql[1] - c.desired_abduction[k];
+    abd = abd * abd;
+    float airt = first ? (air - 0.1f) : 0.f;
+    // foot slip: lower-leg xd shifted to the foot site, xy only
+    V3 off = so.foot_site - so.lower_pos;
+    V3 cr = cross(off, so.lower_ang);
+    float vx = so.lower_vel.x - cr.x, vy = so.lower_vel.y - cr.y;
+    float slip = filt_cm ? (vx * vx + vy * vy) : 0.f;
+    tq = qsum(tq, qm); ja = qsum(ja, qm); mw = qsum(mw, qm); ar = qsum(ar, qm); ss = qsum(ss, qm); sv = qsum(sv, qm);
+    abd = qsum(abd, qm); airt = qsum(airt, qm); slip = qsum(slip, qm);
+    const float cn = brax_norm(V3{oc.command[0], oc.command[1], oc.command[2]});
+    rw[PUPPER_R_TORQUES] = tq;
+    rw[PUPPER_R_JOINT_ACCELERATION] = ja;
+    rw[PUPPER_R_MECHANICAL_WORK] = mw;
+    rw[PUPPER_R_ACTION_RATE] = ar;
+    rw[PUPPER_R_STAND_STILL] = ss * (cn < 0.1f ? 1.f : 0.f);
+    rw[PUPPER_R_STAND_STILL_JOINT_VELOCITY] = sv * (cn < c.stand_still_command_threshold ? 1.f : 0.f);
+    rw[PUPPER_R_ABDUCTION_ANGLE] = abd;
+    rw[PUPPER_R_FEET_AIR_TIME] = airt * (cn > 0.05f ? 1.f : 0.f);
+    rw[PUPPER_R_FOOT_SLIP] = slip;
+    rw[PUPPER_R_TERMINATION] = (done && step0 < c.early_termination_step_threshold) ? 1.f : 0.f;
+    rw[PUPPER_R_KNEE_COLLISION] = so.knee_hits;
+    rw[PUPPER_R_BODY_COLLISION] = so.torso_hits;
+  }
+  float total = 0.f;
+#pragma unroll
+  for (int i = 0; i < PUPPER_NREWARD; i++) { rw[i] = __fmul_rn(rw[i], c.reward_scales[i]); total = __fadd_rn(total, rw[i]); }
+  float reward = fminf(fmaxf(total * dtenv, 0.f), 10000.f);
+  float fdone = done ? 1.f : 0.f;
+  const float total_dist = brax_norm(so.torso_pos);
+
+  // ---- S10 bookkeeping, S11 resampling ------------------------------------------------------------------------------
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int u = 3 * k + j;
+    p.st.last_act[(size_t)u * stride + e] = act[j];
+    p.st.last_vel[(size_t)u * stride + e] = L.vl[j];
+  }
+  p.st.feet_air_time[(size_t)k * stride + e] = filt_mm ? 0.f : air;
+  const uint32_t cbits = (__ballot_sync(qm, contact) >> qbase) & 0xFu;
+  int step = step0 + 1;
+  const bool resample = step > c.resample_velocity_step;
+  if (resample) {
+    float cmd[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
+    if (k == 0) { sample_command(c, cmd_rng, cmd); sample_body_orientation(c, cmd_rng, dz); }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float cv = __shfl_sync(qm, cmd[i], qbase), dv = __shfl_sync(qm, dz[i], qbase);
+      if (k == i) { p.st.command[(size_t)i * stride + e] = cv; p.st.desired_world_z[(size_t)i * stride + e] = dv; }
+    }
+  }
+  if (done || resample) step = 0;
+  if (k == 0) {
+    p.st.last_contact[e] = cbits;
+    p.st.step[e] = step;
+    p.st.kick[e] = kick0; p.st.kick[stride + e] = kick1;
+  }
+
+  // ---- fused brax EpisodeWrapper + AutoResetWrapper ---------------------------------------------------
+  if (p.has_ep) {
+    const int es_ = p.ep.stride;
+    const float prev_done = p.ep.episode_done[e];
+    const float keep = prev_done != 0.f ? 0.f : 1.f;
+    int steps = p.ep.steps[e];
+    if (prev_done != 0.f) steps = 0;
+    steps += c.action_repeat;
+    const bool trunc = steps >= c.episode_length;
+    const float truncation = (trunc && !done) ? 1.f : 0.f;
+    if (trunc) fdone = 1.f;
+    const float sum_reward = (p.ep.sum_reward[e] + reward) * keep;
+    const float length = (p.ep.length[e] + (float)c.action_repeat) * keep;
+    float ep_metric[5];  // this lane's metric rows i = k (mod 4)
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+      int i = k + 4 * t;
+      ep_metric[t] = 0.f;
+      if (i < PUPPER_NMETRIC) {
+        float mv = total_dist;
+#pragma unroll
+        for (int q = 0; q < PUPPER_NREWARD; q++) if (q + 1 == i) mv = rw[q];
+        float v = (p.ep.sum_metrics[(size_t)i * es_ + e] + mv) * keep;
+        p.ep.sum_metrics[(size_t)i * es_ + e] = v;
+        ep_metric[t] = v;
+      }
+    }
+    __syncwarp(qm);
+    if (k == 0) {
+      p.ep.steps[e] = steps; p.ep.truncation[e] = truncation; p.ep.sum_reward[e] = sum_reward; p.ep.length[e] = length;
+      p.ep.episode_done[e] = fdone;
+    }
+    if (p.ep.totals) {
+      if (fdone != 0.f) {  // completed episode: add its sums to the device accumulator (all-reduced by the host side)
+        if (k == 0) { atomicAdd(p.ep.totals + 0, 1.f); atomicAdd(p.ep.totals + 1, sum_reward); atomicAdd(p.ep.totals + 2, length); atomicAdd(p.ep.totals + 22, done ? 1.f : 0.f); }
+#pragma unroll
+        for (int t = 0; t < 5; t++) if (k + 4 * t < PUPPER_NMETRIC) atomicAdd(p.ep.totals + 3 + k + 4 * t, ep_metric[t]);
+      }
+    }
+    if (fdone != 0.f) {  // AutoResetWrapper: restore the first pipeline state and first obs
+      for (int i = k; i < PUPPER_NQ; i += 4) p.st.qpos[(size_t)i * stride + e] = p.ep.first_qpos[(size_t)i * es_ + e];
+      for (int i = k; i < PUPPER_NV; i += 4) {
+        p.st.qvel[(size_t)i * stride + e] = p.ep.first_qvel[(size_t)i * es_ + e];
+        p.st.qacc_warmstart[(size_t)i * stride + e] = p.ep.first_warmstart[(size_t)i * es_ + e];
+      }
+      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i];
+    }
+  }
+
+  // ---- S12 outputs ------------------------------------------------------------------------------------------------------
+  if (k == 0) { p.out.reward[e] = reward; p.out.done[e] = fdone; p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
+#pragma unroll
+  for (int q = 0; q < PUPPER_NREWARD; q++) if ((q & 3) == k) p.out.metrics[(size_t)e * PUPPER_NMETRIC + 1 + q] = rw[q];
+}
+
+}  // namespace pupper
+
+// =====================================================================================================================
+// C ABI
+// =====================================================================================================================
+struct PupperModel {
+  int device;
+  PupperModelDesc *d_desc;
+  PupperEnvCfg *d_cfg;
+  PupperModelDesc h_desc;
+  PupperEnvCfg h_cfg;
+  int last_launches;
+};
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return PUPPER_ECUDA;
+}
+
+extern "C" {
+
+int pupper_abi_version(void) { return PUPPER_ABI_VERSION; }
+
+const char *pupper_strerror(int code) {
+  switch (code) {
+    case PUPPER_OK: return "ok";
+    case PUPPER_EINVAL: return "invalid argument";
+    case PUPPER_EUNSUPPORTED: return "model or configuration outside the supported family";
+    case PUPPER_ECUDA: return "CUDA runtime error (see pupper_last_cuda_error)";
+    case PUPPER_ENOMEM: return "out of memory";
+    case PUPPER_EVERSION: return "ABI version mismatch";
+    default: return "unknown error";
+  }
+}
+
+const char *pupper_last_cuda_error(void) { return g_cuda_err; }
+
+int pupper_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(PupperModelDesc);
+    case 1: return (int)sizeof(PupperEnvCfg);
+    case 2: return (int)sizeof(PupperState);
+    case 3: return (int)sizeof(PupperDR);
+    case 4: return (int)sizeof(PupperStepOut);
+    case 5: return (int)sizeof(PupperEpisode);
+    default: return -1;
+  }
+}
+
+int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, int device, PupperModel **out) {
+  if (!desc || !cfg || !out) return PUPPER_EINVAL;
+  if (desc->abi_version != PUPPER_ABI_VERSION || cfg->abi_version != PUPPER_ABI_VERSION) return PUPPER_EVERSION;
+  if (desc->iterations != 1 || cfg->threefry_partitionable != 1) return PUPPER_EUNSUPPORTED;
+  if (desc->max_geom_pairs < 1 || desc->max_geom_pairs > 4) return PUPPER_EUNSUPPORTED;  // one narrow phase per lane
+  if (desc->max_contact_points < 1 || desc->max_contact_points > PUPPER_MAX_CON) return PUPPER_EUNSUPPORTED;
+  if (desc->nbox < 0 || desc->nbox > PUPPER_MAX_BOX) return PUPPER_EUNSUPPORTED;
+  if (cfg->observation_history < 1 || cfg->n_frames < 1) return PUPPER_EINVAL;
+  if (cfg->n_latency < 1 || cfg->n_latency > PUPPER_MAX_LAT || cfg->n_imu_latency < 1 || cfg->n_imu_latency > PUPPER_MAX_LAT) return PUPPER_EINVAL;
+  for (int i = 1; i < PUPPER_NU; i++)  // the DR contract carries one kp / kd per env
+    if (desc->act_gain[i] != desc->act_gain[0] || desc->act_bias2[i] != desc->act_bias2[0] || desc->act_bias1[i] != -desc->act_gain[i]) return PUPPER_EUNSUPPORTED;
+  for (int b = 1; b < PUPPER_NBODY; b++) {
+    int expect = b == 1 ? 0 : ((b - 2) % 3 == 0 ? 1 : b - 1);
+    if (desc->body_parent[b] != expect) return PUPPER_EUNSUPPORTED;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  PupperModel *m = new (std::nothrow) PupperModel();
+  if (!m) return PUPPER_ENOMEM;
+  m->device = device;
+  m->h_desc = *desc;
+  m->h_cfg = *cfg;
+  m->last_launches = 0;
+  e = cudaMalloc(&m->d_desc, sizeof(PupperModelDesc));
+  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc"); }
+  e = cudaMalloc(&m->d_cfg, sizeof(PupperEnvCfg));
+  if (e != cudaSuccess) { cudaFree(m->d_desc); delete m; return cuda_fail(e, "cudaMalloc"); }
+  e = cudaMemcpy(m->d_desc, desc, sizeof(PupperModelDesc), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_cfg, cfg, sizeof(PupperEnvCfg), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(m->d_desc); cudaFree(m->d_cfg); delete m; return cuda_fail(e, "cudaMemcpy"); }
+  *out = m;
+  return PUPPER_OK;
+}
+
+int pupper_model_destroy(PupperModel *m) {
+  if (!m) return PUPPER_EINVAL;
+  cudaSetDevice(m->device);
+  cudaFree(m->d_desc);
+  cudaFree(m->d_cfg);
+  delete m;
+  return PUPPER_OK;
+}
+
+static int check_common(const PupperModel *model, int n_envs, const PupperDR *dr, const PupperState *st, const PupperStepOut *out,
+                        const PupperEpisode *ep) {
+  if (!model || !st || !out || n_envs <= 0) return PUPPER_EINVAL;
+  if (st->stride < n_envs) return PUPPER_EINVAL;
+  if (!st->qpos || !st->qvel || !st->qacc_warmstart || !st->rng || !st->last_act || !st->action_buffer || !st->imu_buffer ||
+      !st->last_vel || !st->command || !st->desired_world_z || !st->last_contact || !st->feet_air_time || !st->step || !st->kick || !st->obs)
+    return PUPPER_EINVAL;
+  if (!out->reward || !out->done || !out->metrics) return PUPPER_EINVAL;
+  if (dr && (dr->stride < n_envs || !dr->friction || !dr->kp || !dr->kd || !dr->base_ipos || !dr->body_inertia || !dr->body_mass)) return PUPPER_EINVAL;
+  if (ep && (ep->stride < n_envs || !ep->first_qpos || !ep->first_qvel || !ep->first_warmstart || !ep->first_obs || !ep->steps ||
+             !ep->truncation || !ep->sum_reward || !ep->length || !ep->sum_metrics || !ep->episode_done))
+    return PUPPER_EINVAL;
+  return PUPPER_OK;
+}
+
+static pupper::KParams make_params(const PupperModel *model, int n_envs, const PupperDR *dr, const PupperState *st, const float *action,
+                                   const uint32_t *keys, const PupperStepOut *out, const PupperEpisode *ep) {
+  pupper::KParams p;
+  memset(&p, 0, sizeof(p));
+  p.model = model->d_desc;
+  p.cfg = model->d_cfg;
+  p.n_envs = n_envs;
+  p.st = *st;
+  if (dr) { p.dr = *dr; p.has_dr = 1; }
+  p.action = action;
+  p.keys = keys;
+  p.out = *out;
+  if (ep) { p.ep = *ep; p.has_ep = 1; }
+  return p;
+}
+
+static bool wants_debug(const PupperStepOut *o) {
+  return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc;
+}
+
+int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, const PupperDR *dr, PupperState *state, PupperStepOut *out,
+                 PupperEpisode *episode, pupper_stream_t stream) {
+  int rc = check_common(model, n_envs, dr, state, out, episode);
+  if (rc != PUPPER_OK) return rc;
+  if (!keys) return PUPPER_EINVAL;
+  if (wants_debug(out) && (!out->dbg_x_pos || !out->dbg_x_rot || !out->dbg_xd_vel || !out->dbg_xd_ang)) { if (out->dbg_x_pos) return PUPPER_EINVAL; }
+  pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode);
+  const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, 0, s>>>(p);
+  else pupper::env_kernel<true, false><<<grid, pupper::kBlock, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pupper_reset launch");
+  const_cast<PupperModel *>(model)->last_launches = 1;
+  return PUPPER_OK;
+}
+
+int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, PupperState *state, const float *action, PupperStepOut *out,
+                PupperEpisode *episode, pupper_stream_t stream) {
+  int rc = check_common(model, n_envs, dr, state, out, episode);
+  if (rc != PUPPER_OK) return rc;
+  if (!action) return PUPPER_EINVAL;
+  pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode);
+  const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, 0, s>>>(p);
+  else pupper::env_kernel<false, false><<<grid, pupper::kBlock, 0, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "pupper_step launch");
+  const_cast<PupperModel *>(model)->last_launches = 1;
+  return PUPPER_OK;
+}
+
+int pupper_last_launch_count(const PupperModel *model) { return model ? model->last_launches : PUPPER_EINVAL; }
+
+int pupper_state_rows(const PupperEnvCfg *cfg, int32_t *rows_out) {
+  if (!cfg || !rows_out) return PUPPER_EINVAL;
+  const int32_t rows[14] = {PUPPER_NQ, PUPPER_NV, PUPPER_NV, 2, PUPPER_NU, PUPPER_NU * cfg->n_latency, 6 * cfg->n_imu_latency, PUPPER_NU, 3, 3, 1, 4, 1, 2};
+  for (int i = 0; i < 14; i++) rows_out[i] = rows[i];
+  return PUPPER_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1125 @@
+// pupper_kernel.cuh -- the batched PupperV3Env reset/step kernel for sm_100a.
+//
+// Mapping: FOUR LANES PER ENV ("quad"), lane k of a quad owns leg k (3 bodies, 3 hinge dofs, the knee
+// and foot collision spheres, the foot site, 3 action/observation channels); the floating base is
+// replicated in the 4 lanes and combined with 2-step xor-shuffle butterflies (bitwise identical in
+// all 4 lanes).  8 envs per warp, state in SoA so that a warp's 8 envs x 4 legs touch 4 32-byte
+// sectors per row.  Per-env DR leaves, sphere centres and the active-contact list live in shared
+// memory; everything else stays in registers.  The 18x18 joint-space matrices (M and the Newton
+// Hessian) are never formed densely: the kinematic tree gives them an arrow structure
+// [base 6x6 | 4 x (3x6 coupling, 3x3 leg)] that is factorised leaves-first (per-lane 3x3 Cholesky,
+// Schur complement reduced over the quad, replicated 6x6 Cholesky).  Only a leg-leg sphere contact
+// couples two legs; that rare case gathers the system to lane 0 of the quad and solves it densely.
+//
+// What is computed is the reference's PupperV3Env.step (pupperv3_mjx/environment.py:348-483) with the
+// physics it delegates to brax/mjx.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include "../../include/pupper_env.h"
+#include "pupper_math.cuh"
+
+namespace pupper {
+
+constexpr int kBlock = 128;           // threads per CTA
+constexpr int kEnvsPerBlock = kBlock / 4;
+constexpr int kMaxCon = 5 + 3;        // == PUPPER_MAX_CON
+constexpr float kMinVal = 1e-15f, kMinImp = 1e-4f, kMaxImp = 0.9999f;
+constexpr float kInf = 3.0e38f;
+
+struct KParams {
+  const PupperModelDesc *model;  // device copies
+  const PupperEnvCfg *cfg;
+  int n_envs;
+  PupperState st;
+  PupperDR dr;
+  int has_dr;
+  const float *action;
+  const uint32_t *keys;  // reset only
+  PupperStepOut out;
+  PupperEpisode ep;
+  int has_ep;
+};
+
+struct ContactSlot {  // one ACTIVE contact (dist < 0) of an env, shared by the quad
+  float r[3];       // contact point relative to the subtree COM
+  float frame[9];   // rows: normal (geom1 -> geom2), tangent 1, tangent 2
+  float mu, D, b, kimp;  // friction, efc_D of its 4 pyramid rows, damping gain, k*imp*dist
+  float dist;
+  int code1, code2;  // leg*4 + depth (1: link2 / knee sphere, 2: link3 / foot sphere) or -1 for the world
+  int s1, s2;        // sphere indices (or -1) for the collision rewards
+};
+
+struct EnvShared {
+  float mass[13], inertia[39], ipos[3], friction, kp, kd;  // DR leaves (or nominal values)
+  float sph[8][3];
+  ContactSlot con[kMaxCon];
+  int ncon;
+};
+
+struct BlockShared {
+  PupperModelDesc m;
+  PupperEnvCfg c;
+  EnvShared env[kEnvsPerBlock];
+};
+
+__device__ __forceinline__ float qsum(float v, unsigned qm) {
+  v += __shfl_xor_sync(qm, v, 1);
+  v += __shfl_xor_sync(qm, v, 2);
+  return v;
+}
+__device__ __forceinline__ V3 qsum3(V3 v, unsigned qm) { return V3{qsum(v.x, qm), qsum(v.y, qm), qsum(v.z, qm)}; }
+__device__ __forceinline__ S6 qsum6(S6 v, unsigned qm) { return S6{qsum3(v.a, qm), qsum3(v.l, qm)}; }
+__device__ __forceinline__ float qbcast(float v, int src, unsigned qm, int qbase) { return __shfl_sync(qm, v, qbase + src); }
+
+// Arrow-structured symmetric matrix over (base 6 | leg 3), one leg per lane.
+struct TreeMat {
+  float B[21];     // base block, packed lower triangle, row-major: (i,j) at i*(i+1)/2+j   (replicated)
+  float C[3][6];   // leg-base coupling
+  float D[6];      // leg block, packed lower triangle
+};
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// y = A x for the arrow matrix (A.B must already hold the full base block)
+__device__ __forceinline__ void tree_matvec(const TreeMat &A, const float xb[6], const float xl[3], float yb[6], float yl[3], unsigned qm) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) s = fmaf(A.D[i >= j ? tri(i, j) : tri(j, i)], xl[i], s);
+#pragma unroll
+    for (int d = 0; d < 6; d++) s = fmaf(A.C[j][d], xb[d], s);
+    yl[j] = s;
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) s = fmaf(A.C[j][d], xl[j], s);
+    s = qsum(s, qm);
+#pragma unroll
+    for (int i = 0; i < 6; i++) s = fmaf(A.B[i >= d ? tri(i, d) : tri(d, i)], xb[i], s);
+    yb[d] = s;
+  }
+}
+
+// In-place leaves-first Cholesky.  On exit: D = L_k (3x3 lower), C = Y_k = L_k^-1 C_k,
+// B = chol(B + sum_k (Badd_k - Y_k^T Y_k)) (lower, replicated).  Badd may be null.
+__device__ __forceinline__ void tree_factor(TreeMat &A, const float *Badd, unsigned qm) {
+  float l00 = sqrtf(A.D[0]);
+  float i00 = 1.f / l00;
+  float l10 = A.D[1] * i00, l20 = A.D[3] * i00;
+  float l11 = sqrtf(A.D[2] - l10 * l10);
+  float i11 = 1.f / l11;
+  float l21 = (A.D[4] - l20 * l10) * i11;
+  float l22 = sqrtf(A.D[5] - l20 * l20 - l21 * l21);
+  float i22 = 1.f / l22;
+  A.D[0] = l00; A.D[1] = l10; A.D[2] = l11; A.D[3] = l20; A.D[4] = l21; A.D[5] = l22;
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float y0 = A.C[0][d] * i00;
+    float y1 = (A.C[1][d] - l10 * y0) * i11;
+    float y2 = (A.C[2][d] - l20 * y0 - l21 * y1) * i22;
+    A.C[0][d] = y0; A.C[1][d] = y1; A.C[2][d] = y2;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      float s = Badd ? Badd[tri(i, j)] : 0.f;
+      s = fmaf(-A.C[0][i], A.C[0][j], s);
+      s = fmaf(-A.C[1][i], A.C[1][j], s);
+      s = fmaf(-A.C[2][i], A.C[2][j], s);
+      A.B[tri(i, j)] += qsum(s, qm);
+    }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      float s = A.B[tri(i, j)];
+#pragma unroll
+      for (int p = 0; p < j; p++) s = fmaf(-A.B[tri(i, p)], A.B[tri(j, p)], s);
+      A.B[tri(i, j)] = (i == j) ? sqrtf(s) : s / A.B[tri(j, j)];
+    }
+}
+
+// x = A^-1 g with the factor produced by tree_factor
+__device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], const float gl[3], float xb[6], float xl[3], unsigned qm) {
+  float z0 = gl[0] / F.D[0];
+  float z1 = (gl[1] - F.D[1] * z0) / F.D[2];
+  float z2 = (gl[2] - F.D[3] * z0 - F.D[4] * z1) / F.D[5];
+  float y[6];
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float s = fmaf(F.C[0][d], z0, fmaf(F.C[1][d], z1, F.C[2][d] * z2));
+    y[d] = gb[d] - qsum(s, qm);
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float s = y[i];
+#pragma unroll
+    for (int p = 0; p < i; p++) s = fmaf(-F.B[tri(i, p)], y[p], s);
+    y[i] = s / F.B[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = y[i];
+#pragma unroll
+    for (int p = i + 1; p < 6; p++) s = fmaf(-F.B[tri(p, i)], xb[p], s);
+    xb[i] = s / F.B[tri(i, i)];
+  }
+  float w0 = z0, w1 = z1, w2 = z2;
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    w0 = fmaf(-F.C[0][d], xb[d], w0);
+    w1 = fmaf(-F.C[1][d], xb[d], w1);
+    w2 = fmaf(-F.C[2][d], xb[d], w2);
+  }
+  xl[2] = w2 / F.D[5];
+  xl[1] = (w1 - F.D[4] * xl[2]) / F.D[2];
+  xl[0] = (w0 - F.D[1] * xl[1] - F.D[3] * xl[2]) / F.D[0];
+}
+
+// solref/solimp -> (k, b, imp) at constraint violation `pos`
+__device__ __forceinline__ void kbi(const float *solref, const float *solimp, float timestep, float pos, float &k, float &b, float &imp) {
+  float timeconst = fmaxf(solref[0], 2.f * timestep), dampratio = solref[1];
+  float dmin = fminf(fmaxf(solimp[0], kMinImp), kMaxImp), dmax = fminf(fmaxf(solimp[1], kMinImp), kMaxImp);
+  float width = fmaxf(kMinVal, solimp[2]), mid = fminf(fmaxf(solimp[3], kMinImp), kMaxImp), power = fmaxf(1.f, solimp[4]);
+  k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  b = 2.f / (dmax * timeconst);
+  if (solref[0] <= 0.f) k = -solref[0] / (dmax * dmax);
+  if (solref[1] <= 0.f) b = -solref[1] / dmax;
+  float x = fabsf(pos) / width;
+  float ia, ib;
+  if (power == 2.f) {
+    ia = (1.f / mid) * (x * x);
+    ib = 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
+  } else {
+    ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+    ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  }
+  float y = x < mid ? ia : ib;
+  float im = dmin + y * (dmax - dmin);
+  im = fminf(fmaxf(im, dmin), dmax);
+  if (x > 1.f) im = dmax;
+  imp = im;
+}
+
+__device__ __forceinline__ void make_frame(V3 n, float fr[9]) {
+  V3 a = n;
+  normalize3(a);
+  V3 b = fabsf(a.y) < 0.5f ? V3{0.f, 1.f, 0.f} : V3{0.f, 0.f, 1.f};
+  float ab = dot(a, b);
+  b = b - ab * a;
+  normalize3(b);
+  V3 c = cross(a, b);
+  fr[0] = a.x; fr[1] = a.y; fr[2] = a.z; fr[3] = b.x; fr[4] = b.y; fr[5] = b.z; fr[6] = c.x; fr[7] = c.y; fr[8] = c.z;
+}
+
+// sphere vs box (box = 6-face polytope).  Returns dist; pos / n in world frame.
+__device__ __forceinline__ float sphere_box(V3 cw, float radius, const float *bpos, const float *bmat, const float *size, V3 &pos_out, V3 &n_out) {
+  V3 d = cw - V3{bpos[0], bpos[1], bpos[2]};
+  V3 c = V3{bmat[0] * d.x + bmat[3] * d.y + bmat[6] * d.z, bmat[1] * d.x + bmat[4] * d.y + bmat[7] * d.z,
+            bmat[2] * d.x + bmat[5] * d.y + bmat[8] * d.z};
+  // faces in MJX order: -y, -z, +x, +y, +z, -x ; support_f = (c - n r - v0).n
+  const float sx = size[0], sy = size[1], sz = size[2];
+  float sup[6] = {-(c.y) - radius - sy, -(c.z) - radius - sz, c.x - radius - sx, c.y - radius - sy, c.z - radius - sz, -(c.x) - radius - sx};
+  int best = 0;
+  float bs = 0.f;
+#pragma unroll
+  for (int f = 0; f < 6; f++) {
+    float s = sup[f] >= 0.f ? -1e12f : sup[f];
+    if (f == 0 || s > bs) { best = f; bs = s; }
+  }
+  // face axis / sign and its two in-plane axes; vertices listed in the MJX winding
+  int ax = (best == 2 || best == 5) ? 0 : ((best == 0 || best == 3) ? 1 : 2);
+  float sgn = (best == 2 || best == 3 || best == 4) ? 1.f : -1.f;
+  float half[3] = {sx, sy, sz};
+  float cc[3] = {c.x, c.y, c.z};
+  float pt[3] = {c.x, c.y, c.z};
+  pt[ax] = sgn * half[ax];  // projection of the centre on the face plane
+  // face vertex loops (vertex id v = 4*ix + 2*iy + iz)
+  const int FACE[6][4] = {{0, 4, 5, 1}, {0, 2, 6, 4}, {6, 7, 5, 4}, {2, 3, 7, 6}, {1, 5, 7, 3}, {0, 1, 3, 2}};
+  float fn[3] = {0.f, 0.f, 0.f};
+  fn[ax] = sgn;
+  float fv[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int v = FACE[best][i];
+    fv[i][0] = (v & 4) ? sx : -sx;
+    fv[i][1] = (v & 2) ? sy : -sy;
+    fv[i][2] = (v & 1) ? sz : -sz;
+  }
+  bool inside = true;
+  int idx = 0;
+  float be = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float *p0 = fv[(i + 3) & 3], *p1 = fv[i];
+    V3 e = V3{p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    V3 en = cross(e, V3{fn[0], fn[1], fn[2]});
+    float ed = dot(V3{pt[0] - p0[0], pt[1] - p0[1], pt[2] - p0[2]}, en);
+    if (!(ed <= 0.f)) inside = false;
+    bool degenerate = (en.x == 0.f && en.y == 0.f && en.z == 0.f);
+    float v = (degenerate || ed < 0.f) ? 1e12f : ed;
+    if (i == 0 || v < be) { be = v; idx = i; }
+  }
+  if (!inside) {
+    const float *a = fv[(idx + 3) & 3], *b = fv[idx];
+    V3 ab = V3{b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+    V3 pa = V3{pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+    float t = dot(pa, ab) / (dot(ab, ab) + 1e-6f);
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    pt[0] = a[0] + t * ab.x; pt[1] = a[1] + t * ab.y; pt[2] = a[2] + t * ab.z;
+  }
+  V3 n = V3{pt[0] - cc[0], pt[1] - cc[1], pt[2] - cc[2]};
+  float dn = normalize3(n);
+  V3 p = V3{(pt[0] + (cc[0] + n.x * radius)) * 0.5f, (pt[1] + (cc[1] + n.y * radius)) * 0.5f, (pt[2] + (cc[2] + n.z * radius)) * 0.5f};
+  n_out = V3{bmat[0] * n.x + bmat[1] * n.y + bmat[2] * n.z, bmat[3] * n.x + bmat[4] * n.y + bmat[5] * n.z, bmat[6] * n.x + bmat[7] * n.y + bmat[8] * n.z};
+  pos_out = V3{bmat[0] * p.x + bmat[1] * p.y + bmat[2] * p.z + bpos[0], bmat[3] * p.x + bmat[4] * p.y + bmat[5] * p.z + bpos[1],
+               bmat[6] * p.x + bmat[7] * p.y + bmat[8] * p.z + bpos[2]};
+  return dn - radius;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-lane physics state
+// ---------------------------------------------------------------------------------------------------
+struct LaneState {
+  float qb[7];      // base position + quaternion (replicated)
+  float ql[3];      // this leg's joint angles
+  float vb[6], vl[3];
+  float wb[6], wl[3];  // qacc_warmstart
+  float ctrl[3];
+};
+
+// quantities of the forward pass that the env level reads after the last substep ("stale" mix)
+struct StaleOut {
+  V3 torso_pos;
+  Q4 torso_rot;
+  V3 torso_ang, torso_vel;   // xd of the torso (body-origin world velocity)
+  V3 com;
+  V3 foot_site;              // this leg's foot site position
+  V3 lower_pos;              // xpos of this leg's lower-leg body
+  V3 lower_ang, lower_vel;   // xd of the lower leg
+  float frc[3];              // qfrc_actuator of this leg
+  float knee_hits, torso_hits;  // collision reward counters (whole env, replicated)
+};
+
+struct DbgOut {  // only filled when DBG
+  V3 pos[3]; Q4 rot[3]; V3 ang[3], vel[3];
+  float qacc_b[6], qacc_l[3];
+};
+
+struct Row {  // one scalar constraint row handled by this lane
+  float D, aref, jaref, jv;
+};
+
+// Per-lane participation in contact c: bits 0-1 depth as body1 (-), bits 2-3 depth as body2 (+).
+__device__ __forceinline__ int participation(const ContactSlot &s, int k) {
+  int p = 0;
+  if (s.code1 >= 0 && (s.code1 >> 2) == k) p |= (s.code1 & 3);
+  if (s.code2 >= 0 && (s.code2 >> 2) == k) p |= (s.code2 & 3) << 2;
+  return p;
+}
+
+// jq[c] = Jc v (normal, t1, t2 components) for every active contact, replicated over the quad
+__device__ __forceinline__ void contact_jv(const EnvShared &es, int ncon, const int *part, const S6 cd[3], const V3 ba[3], const V3 bo[3],
+                                           const float vb[6], const float vl[3], float jq[][3], unsigned qm) {
+  S6 W0;
+  W0.a = vb[3] * ba[0] + vb[4] * ba[1] + vb[5] * ba[2];
+  W0.l = V3{vb[0], vb[1], vb[2]} + vb[3] * bo[0] + vb[4] * bo[1] + vb[5] * bo[2];
+  S6 W1 = fma6(vl[1], cd[1], fma6(vl[0], cd[0], W0));
+  S6 W2 = fma6(vl[2], cd[2], W1);
+#pragma unroll
+  for (int c = 0; c < kMaxCon; c++) {
+    if (c < ncon) {
+      const ContactSlot &s = es.con[c];
+      V3 r = V3{s.r[0], s.r[1], s.r[2]};
+      int d1 = part[c] & 3, d2 = (part[c] >> 2) & 3;
+      V3 pv = V3{0.f, 0.f, 0.f};
+      if (d2) { const S6 &W = d2 == 1 ? W1 : W2; pv = pv + (W.l + cross(W.a, r)); }
+      if (d1) { const S6 &W = d1 == 1 ? W1 : W2; pv = pv - (W.l + cross(W.a, r)); }
+      pv = qsum3(pv, qm);
+      jq[c][0] = s.frame[0] * pv.x + s.frame[1] * pv.y + s.frame[2] * pv.z;
+      jq[c][1] = s.frame[3] * pv.x + s.frame[4] * pv.y + s.frame[5] * pv.z;
+      jq[c][2] = s.frame[6] * pv.x + s.frame[7] * pv.y + s.frame[8] * pv.z;
+    }
+  }
+}
+
+// friction-loss row zone at residual x: 1 quadratic, 2 linear (x <= -R f), 3 linear (x >= R f)
+__device__ __forceinline__ int fzone(float x, float rf) { return x <= -rf ? 2 : (x >= rf ? 3 : 1); }
+
+struct LSPoint {
+  float alpha, cost, d0, d1;
+};
+__device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
+  return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One mjx.forward for the env of this quad.  Outputs qacc (ab, al).
+// ---------------------------------------------------------------------------------------------------
+template <bool DBG>
+__device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, LaneState &L, int k, unsigned qm, int qbase,
+                                     float ab[6], float al[3], bool want_stale, StaleOut &so, DbgOut *dbg) {
+  const PupperModelDesc &m = sh.m;
+  const int b0 = 2 + 3 * k;   // first body of this leg
+  const float dt = m.timestep;
+
+  // ---- kinematics (A.2) ------------------------------------------------------------------------
+  Q4 q1 = qnormalize(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]});
+  L.qb[3] = q1.w; L.qb[4] = q1.x; L.qb[5] = q1.y; L.qb[6] = q1.z;
+  const V3 p1 = V3{L.qb[0], L.qb[1], L.qb[2]};
+  const M3 R1 = qmat(q1);
+  V3 pos[3], axis[3], xip[3];
+  Q4 rot[3];
+  float Iw[3][6];  // rotated body inertia (xx,yy,zz,xy,xz,yz)
+  {
+    V3 pp = p1;
+    Q4 pq = q1;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int b = b0 + j;
+      pos[j] = pp + rotate(V3{m.body_pos[b][0], m.body_pos[b][1], m.body_pos[b][2]}, pq);
+      Q4 q = qmul(pq, Q4{m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
+      axis[j] = rotate(V3{0.f, 0.f, 1.f}, q);
+      float sn, cs;
+      sincosf(L.ql[j] * 0.5f, &sn, &cs);
+      rot[j] = qmul(q, Q4{cs, 0.f, 0.f, sn});
+      xip[j] = pos[j] + rotate(V3{m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]}, rot[j]);
+      M3 Ri = qmat(qmul(rot[j], Q4{m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]}));
+      const float *di = &es.inertia[(b - 1) * 3];
+      Iw[j][0] = Ri.m[0] * di[0] * Ri.m[0] + Ri.m[1] * di[1] * Ri.m[1] + Ri.m[2] * di[2] * Ri.m[2];
+      Iw[j][1] = Ri.m[3] * di[0] * Ri.m[3] + Ri.m[4] * di[1] * Ri.m[4] + Ri.m[5] * di[2] * Ri.m[5];
+      Iw[j][2] = Ri.m[6] * di[0] * Ri.m[6] + Ri.m[7] * di[1] * Ri.m[7] + Ri.m[8] * di[2] * Ri.m[8];
+      Iw[j][3] = Ri.m[0] * di[0] * Ri.m[3] + Ri.m[1] * di[1] * Ri.m[4] + Ri.m[2] * di[2] * Ri.m[5];
+      Iw[j][4] = Ri.m[0] * di[0] * Ri.m[6] + Ri.m[1] * di[1] * Ri.m[7] + Ri.m[2] * di[2] * Ri.m[8];
+      Iw[j][5] = Ri.m[3] * di[0] * Ri.m[6] + Ri.m[4] * di[1] * Ri.m[7] + Ri.m[5] * di[2] * Ri.m[8];
+      pp = pos[j];
+      pq = rot[j];
+    }
+  }
+  // collision sphere centres (knee on link2, foot on link3) and the foot site
+  V3 sc[2];
+  sc[0] = pos[1] + rotate(V3{m.sphere_pos[2 * k][0], m.sphere_pos[2 * k][1], m.sphere_pos[2 * k][2]}, rot[1]);
+  sc[1] = pos[2] + rotate(V3{m.sphere_pos[2 * k + 1][0], m.sphere_pos[2 * k + 1][1], m.sphere_pos[2 * k + 1][2]}, rot[2]);
+  es.sph[2 * k][0] = sc[0].x; es.sph[2 * k][1] = sc[0].y; es.sph[2 * k][2] = sc[0].z;
+  es.sph[2 * k + 1][0] = sc[1].x; es.sph[2 * k + 1][1] = sc[1].y; es.sph[2 * k + 1][2] = sc[1].z;
+  // base inertial frame
+  const V3 xip_b = p1 + rotate(V3{es.ipos[0], es.ipos[1], es.ipos[2]}, q1);
+  float Iwb[6];
+  {
+    M3 Ri = qmat(qmul(q1, Q4{m.body_iquat[1][0], m.body_iquat[1][1], m.body_iquat[1][2], m.body_iquat[1][3]}));
+    const float *di = &es.inertia[0];
+    Iwb[0] = Ri.m[0] * di[0] * Ri.m[0] + Ri.m[1] * di[1] * Ri.m[1] + Ri.m[2] * di[2] * Ri.m[2];
+    Iwb[1] = Ri.m[3] * di[0] * Ri.m[3] + Ri.m[4] * di[1] * Ri.m[4] + Ri.m[5] * di[2] * Ri.m[5];
+    Iwb[2] = Ri.m[6] * di[0] * Ri.m[6] + Ri.m[7] * di[1] * Ri.m[7] + Ri.m[8] * di[2] * Ri.m[8];
+    Iwb[3] = Ri.m[0] * di[0] * Ri.m[3] + Ri.m[1] * di[1] * Ri.m[4] + Ri.m[2] * di[2] * Ri.m[5];
+    Iwb[4] = Ri.m[0] * di[0] * Ri.m[6] + Ri.m[1] * di[1] * Ri.m[7] + Ri.m[2] * di[2] * Ri.m[8];
+    Iwb[5] = Ri.m[3] * di[0] * Ri.m[6] + Ri.m[4] * di[1] * Ri.m[7] + Ri.m[5] * di[2] * Ri.m[8];
+  }
+
+  // ---- subtree COM (A.3): leaf -> root mass-weighted sum, butterfly over the 4 legs --------------
+  const float mb = es.mass[0];
+  float ml[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) ml[j] = es.mass[b0 - 1 + j];
+  V3 C;
+  {
+    V3 pl = ml[1] * xip[1] + ml[2] * xip[2];
+    pl = ml[0] * xip[0] + pl;
+    float msum = ml[0] + (ml[1] + ml[2]);
+    pl = qsum3(pl, qm);
+    msum = qsum(msum, qm);
+    V3 pt = mb * xip_b + pl;
+    float mt = mb + msum;
+    C = mt < kMinVal ? xip_b : V3{pt.x / mt, pt.y / mt, pt.z / mt};
+  }
+
+  // ---- cinert, cdof (A.3) -------------------------------------------------------------------------
+  Inertia ci[3], cib;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    V3 off = xip[j] - C;
+    float mm = ml[j], o2 = dot(off, off);
+    ci[j] = Inertia{Iw[j][0] + mm * (o2 - off.x * off.x), Iw[j][1] + mm * (o2 - off.y * off.y), Iw[j][2] + mm * (o2 - off.z * off.z),
+                    Iw[j][3] - mm * off.x * off.y, Iw[j][4] - mm * off.x * off.z, Iw[j][5] - mm * off.y * off.z, mm * off, mm};
+  }
+  {
+    V3 off = xip_b - C;
+    float o2 = dot(off, off);
+    cib = Inertia{Iwb[0] + mb * (o2 - off.x * off.x), Iwb[1] + mb * (o2 - off.y * off.y), Iwb[2] + mb * (o2 - off.z * off.z),
+                  Iwb[3] - mb * off.x * off.y, Iwb[4] - mb * off.x * off.z, Iwb[5] - mb * off.y * off.z, mb * off, mb};
+  }
+  S6 cd[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) cd[j] = S6{axis[j], cross(axis[j], C - pos[j])};
+  V3 ba[3], bo[3];
+  {
+    V3 ob = C - p1;
+    ba[0] = V3{R1.m[0], R1.m[3], R1.m[6]};
+    ba[1] = V3{R1.m[1], R1.m[4], R1.m[7]};
+    ba[2] = V3{R1.m[2], R1.m[5], R1.m[8]};
+#pragma unroll
+    for (int i = 0; i < 3; i++) bo[i] = cross(ba[i], ob);
+  }
+
+  // ---- velocities, RNE bias forces (A.7) -------------------------------------------------------------
+  S6 cvb;  // base spatial velocity
+  cvb.a = L.vb[3] * ba[0] + L.vb[4] * ba[1] + L.vb[5] * ba[2];
+  cvb.l = V3{L.vb[0], L.vb[1], L.vb[2]} + L.vb[3] * bo[0] + L.vb[4] * bo[1] + L.vb[5] * bo[2];
+  // cdof_dot of the 3 rotational base dofs uses the translational part only: [0, v_lin x a_i]
+  S6 cab;  // base spatial acceleration bias
+  {
+    V3 vt = V3{L.vb[0], L.vb[1], L.vb[2]};
+    V3 w = L.vb[3] * cross(vt, ba[0]) + L.vb[4] * cross(vt, ba[1]) + L.vb[5] * cross(vt, ba[2]);
+    cab.a = V3{0.f, 0.f, 0.f};
+    cab.l = V3{-m.gravity[0], -m.gravity[1], -m.gravity[2]} + w;
+  }
+  S6 cv[3], ca[3];
+  {
+    S6 pv = cvb, pa = cab;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      S6 cdd = motion_cross(pv, cd[j]);
+      cv[j] = fma6(L.vl[j], cd[j], pv);
+      ca[j] = fma6(L.vl[j], cdd, pa);
+      pv = cv[j];
+      pa = ca[j];
+    }
+  }
+  float bias_l[3], bias_b[6];
+  TreeMat M;
+  {
+    // backward pass: composite forces and composite inertias, leaf -> root
+    S6 cf = S6{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}};
+    Inertia crb = Inertia{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, V3{0.f, 0.f, 0.f}, 0.f};
+#pragma unroll
+    for (int j = 2; j >= 0; j--) {
+      S6 f = inert_mul(ci[j], ca[j]) + motion_cross_force(cv[j], inert_mul(ci[j], cv[j]));
+      cf = cf + f;
+      bias_l[j] = dot6(cd[j], cf);
+      crb = crb + ci[j];
+      S6 F = inert_mul(crb, cd[j]);  // crb_cdof of dof j
+#pragma unroll
+      for (int jj = 0; jj <= j; jj++) M.D[tri(j, jj)] = dot6(F, cd[jj]);
+      M.D[tri(j, j)] += m.dof_armature[6 + 3 * k + j];
+      M.C[j][0] = F.l.x; M.C[j][1] = F.l.y; M.C[j][2] = F.l.z;
+#pragma unroll
+      for (int i = 0; i < 3; i++) M.C[j][3 + i] = dot(ba[i], F.a) + dot(bo[i], F.l);
+    }
+    // base: own body + the 4 leg subtrees
+    S6 fb = inert_mul(cib, cab) + motion_cross_force(cvb, inert_mul(cib, cvb));
+    S6 cfb = fb + qsum6(cf, qm);
+    Inertia crbb;
+    crbb.xx = cib.xx + qsum(crb.xx, qm); crbb.yy = cib.yy + qsum(crb.yy, qm); crbb.zz = cib.zz + qsum(crb.zz, qm);
+    crbb.xy = cib.xy + qsum(crb.xy, qm); crbb.xz = cib.xz + qsum(crb.xz, qm); crbb.yz = cib.yz + qsum(crb.yz, qm);
+    crbb.h = cib.h + qsum3(crb.h, qm);
+    crbb.m = cib.m + qsum(crb.m, qm);
+    bias_b[0] = cfb.l.x; bias_b[1] = cfb.l.y; bias_b[2] = cfb.l.z;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bias_b[3 + i] = dot(ba[i], cfb.a) + dot(bo[i], cfb.l);
+    // base block of M: translation dofs cdof = [0, e_d]; rotation dofs cdof = [a_i, a_i x o]
+#pragma unroll
+    for (int i = 0; i < 21; i++) M.B[i] = 0.f;
+    M.B[tri(0, 0)] = crbb.m + m.dof_armature[0];
+    M.B[tri(1, 1)] = crbb.m + m.dof_armature[1];
+    M.B[tri(2, 2)] = crbb.m + m.dof_armature[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      S6 F = inert_mul(crbb, S6{ba[i], bo[i]});
+      M.B[tri(3 + i, 0)] = F.l.x; M.B[tri(3 + i, 1)] = F.l.y; M.B[tri(3 + i, 2)] = F.l.z;
+#pragma unroll
+      for (int ii = 0; ii <= i; ii++) M.B[tri(3 + i, 3 + ii)] = dot(ba[ii], F.a) + dot(bo[ii], F.l);
+      M.B[tri(3 + i, 3 + i)] += m.dof_armature[3 + i];
+    }
+  }
+
+  // ---- actuation, smooth forces (A.7) ---------------------------------------------------------------
+  float frc[3], fs_l[3], fs_b[6];
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int u = 3 * k + j;
+    float f = es.kp * L.ctrl[j] + (-es.kp * L.ql[j] + -es.kd * L.vl[j]);
+    f = fminf(fmaxf(f, m.act_forcerange[u][0]), m.act_forcerange[u][1]);
+    frc[j] = f;
+    fs_l[j] = -m.dof_damping[6 + u] * L.vl[j] - bias_l[j] + f;
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) fs_b[d] = -m.dof_damping[d] * L.vb[d] - bias_b[d];
+
+  // ---- collision (A.5): keep only contacts that can act (dist < 0), at most max_contact_points ------
+  __syncwarp(qm);  // sphere centres visible to the quad
+  int ncon = 0;
+  {
+    float cdist[4];
+    V3 cpos[4], cn[4];
+    int ccode1[4], ccode2[4], cs1[4], cs2[4], ctype[4];
+    int cbox = 0;
+    // plane-sphere: own two spheres against z = 0
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      float r = m.sphere_radius[2 * k + i];
+      float d = sc[i].z - r;
+      cdist[i] = d < 0.f ? d : kInf;
+      cn[i] = V3{0.f, 0.f, 1.f};
+      cpos[i] = sc[i] - (r + 0.5f * d) * cn[i];
+      ccode1[i] = -1; ccode2[i] = k * 4 + 1 + i; cs1[i] = -1; cs2[i] = 2 * k + i; ctype[i] = 0;
+    }
+    cdist[2] = kInf; cdist[3] = kInf;
+    ccode1[2] = ccode2[2] = cs1[2] = cs2[2] = -1; ctype[2] = 1; cpos[2] = cn[2] = V3{0.f, 0.f, 0.f};
+    ccode1[3] = ccode2[3] = cs1[3] = cs2[3] = -1; ctype[3] = 2; cpos[3] = cn[3] = V3{0.f, 0.f, 0.f};
+    const int maxp = m.max_geom_pairs;
+    // sphere-box: broad phase keeps the max_geom_pairs pairs with the smallest bounding-sphere
+    // distance over all 8*nbox pairs (pair index = sphere*nbox + box); lane i runs narrow phase i.
+    if (m.nbox > 0) {
+      const int nbox = m.nbox;
+      uint32_t taken0 = 0u, taken1 = 0u;  // per own sphere, bit per box
+      for (int r = 0; r < maxp && r < 8 * nbox; r++) {
+        float bk = kInf;
+        int bi = 0x7fffffff;
+        for (int i = 0; i < 2; i++) {
+          uint32_t taken = i ? taken1 : taken0;
+          for (int bx = 0; bx < nbox; bx++) {
+            if ((taken >> bx) & 1u) continue;
+            V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sc[i];
+            float rb = sqrtf(m.box_size[bx][0] * m.box_size[bx][0] + m.box_size[bx][1] * m.box_size[bx][1] + m.box_size[bx][2] * m.box_size[bx][2]);
+            float key = sqrtf(dot(d, d)) - (m.sphere_radius[2 * k + i] + rb);
+            int id = (2 * k + i) * nbox + bx;
+            if (key < bk || (key == bk && id < bi)) { bk = key; bi = id; }
+          }
+        }
+#pragma unroll
+        for (int s = 1; s <= 2; s <<= 1) {
+          float ok = __shfl_xor_sync(qm, bk, s);
+          int oi = __shfl_xor_sync(qm, bi, s);
+          if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+        }
+        int sph = bi / nbox, bx = bi - sph * nbox;
+        if ((sph >> 1) == k) { if (sph & 1) taken1 |= 1u << bx; else taken0 |= 1u << bx; }
+        if ((r & 3) == k && r < 4) {  // narrow phase of selected pair r on lane r
+          V3 c = V3{es.sph[sph][0], es.sph[sph][1], es.sph[sph][2]};
+          V3 pp, nn;
+          float d = sphere_box(c, m.sphere_radius[sph], m.box_pos[bx], m.box_mat[bx], m.box_size[bx], pp, nn);
+          cdist[2] = d < 0.f ? d : kInf;
+          cpos[2] = pp; cn[2] = nn;
+          ccode1[2] = (sph >> 1) * 4 + 1 + (sph & 1); ccode2[2] = -1; cs1[2] = sph; cs2[2] = -1; cbox = bx;
+        }
+      }
+    }
+    // sphere-sphere: 24 leg-leg pairs, 6 per lane in MJX pair order; nothing to do unless one penetrates
+    {
+      float pd[6];
+      int pa[6], pb[6];
+      bool any_neg = false;
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        // pair p = 6k+i of the list {(a,b): a<b, a/2 != b/2} in lexicographic order
+        int p = 6 * k + i;
+        int a = p < 6 ? 0 : (p < 12 ? 1 : (p < 16 ? 2 : (p < 20 ? 3 : (p < 22 ? 4 : 5))));
+        int first = a < 2 ? 2 : (a < 4 ? 4 : 6);
+        int base = a == 0 ? 0 : (a == 1 ? 6 : (a == 2 ? 12 : (a == 3 ? 16 : (a == 4 ? 20 : 22))));
+        int b = first + (p - base);
+        V3 d = V3{es.sph[b][0] - es.sph[a][0], es.sph[b][1] - es.sph[a][1], es.sph[b][2] - es.sph[a][2]};
+        pd[i] = sqrtf(dot(d, d)) - (m.sphere_radius[a] + m.sphere_radius[b]);
+        pa[i] = a; pb[i] = b;
+        any_neg |= pd[i] < 0.f;
+      }
+      unsigned anyq = __ballot_sync(qm, any_neg) & qm;
+      if (anyq) {
+        uint32_t taken = 0u;
+        for (int r = 0; r < maxp && r < 24; r++) {
+          float bk = kInf;
+          int bi = 0x7fffffff;
+#pragma unroll
+          for (int i = 0; i < 6; i++)
+            if (!((taken >> i) & 1u) && (pd[i] < bk || (pd[i] == bk && 6 * k + i < bi))) { bk = pd[i]; bi = 6 * k + i; }
+#pragma unroll
+          for (int s = 1; s <= 2; s <<= 1) {
+            float ok = __shfl_xor_sync(qm, bk, s);
+            int oi = __shfl_xor_sync(qm, bi, s);
+            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+          }
+          int owner = min(bi / 6, 3), li = bi - owner * 6;
+          int a = 0, b = 0;
+#pragma unroll
+          for (int i = 0; i < 6; i++) if (i == li) { a = pa[i]; b = pb[i]; }
+          a = __shfl_sync(qm, a, qbase + owner);
+          b = __shfl_sync(qm, b, qbase + owner);
+          if (owner == k) taken |= 1u << li;
+          if ((r & 3) == k && r < 4 && bk < 0.f) {
+            V3 ca_ = V3{es.sph[a][0], es.sph[a][1], es.sph[a][2]}, cb_ = V3{es.sph[b][0], es.sph[b][1], es.sph[b][2]};
+            V3 n = cb_ - ca_;
+            float dn = normalize3(n);
+            if (dn == 0.f) n = V3{1.f, 0.f, 0.f};
+            float d = dn - (m.sphere_radius[a] + m.sphere_radius[b]);
+            cdist[3] = d < 0.f ? d : kInf;
+            cn[3] = n;
+            cpos[3] = ca_ + (m.sphere_radius[a] + d * 0.5f) * n;
+            ccode1[3] = (a >> 1) * 4 + 1 + (a & 1); ccode2[3] = (b >> 1) * 4 + 1 + (b & 1); cs1[3] = a; cs2[3] = b;
+          }
+        }
+      }
+    }
+    // final cut: the max_contact_points smallest dist over [plane 0..7, box 8..11, sphere-sphere 12..15]
+    const int maxc = m.max_contact_points;
+    for (int r = 0; r < maxc; r++) {
+      float bk = kInf;
+      int bi = 0x7fffffff, bl = 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        int id = i < 2 ? 2 * k + i : (i == 2 ? 8 + k : 12 + k);
+        if (cdist[i] < bk || (cdist[i] == bk && id < bi && cdist[i] < kInf)) { bk = cdist[i]; bi = id; bl = i; }
+      }
+      float mk = bk;
+      int mi = bi;
+#pragma unroll
+      for (int s = 1; s <= 2; s <<= 1) {
+        float ok = __shfl_xor_sync(qm, mk, s);
+        int oi = __shfl_xor_sync(qm, mi, s);
+        if (ok < mk || (ok == mk && oi < mi)) { mk = ok; mi = oi; }
+      }
+      if (!(mk < 0.f)) break;  // uniform over the quad
+      if (mi == bi && bk < 0.f) {  // this lane owns the winner: publish slot r
+        ContactSlot &s = es.con[r];
+        V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
+        int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
+        const int bxi = cbox;
+#pragma unroll
+        for (int i = 0; i < 4; i++) if (i == bl) { pp = cpos[i]; nn = cn[i]; c1 = ccode1[i]; c2 = ccode2[i]; s1 = cs1[i]; s2 = cs2[i]; ty = ctype[i]; cdist[i] = kInf; }
+        s.r[0] = pp.x - C.x; s.r[1] = pp.y - C.y; s.r[2] = pp.z - C.z;
+        make_frame(nn, s.frame);
+        // geom friction: one DR draw for every geom (es.friction >= 0) or the model's per-geom values
+        const bool drf = es.friction >= 0.f;
+        float f1 = s1 >= 0 ? (drf ? es.friction : m.sphere_friction[s1]) : (drf ? es.friction : m.floor_friction);
+        float f2 = s2 >= 0 ? (drf ? es.friction : m.sphere_friction[s2]) : (ty == 1 ? (drf ? es.friction : m.box_friction[bxi]) : (drf ? es.friction : m.floor_friction));
+        if (ty == 0) f1 = drf ? es.friction : m.floor_friction;
+        float mu = fmaxf(f1, f2);
+        float w1 = c1 >= 0 ? m.body_invweight0[2 + 3 * (c1 >> 2) + (c1 & 3)] : 0.f;
+        float w2 = c2 >= 0 ? m.body_invweight0[2 + 3 * (c2 >> 2) + (c2 & 3)] : 0.f;
+        float t = w1 + w2;
+        float invw = t + mu * mu * t;
+        invw = invw * 2.f * mu * mu / m.impratio;
+        const float *solref = ty == 0 ? m.plane_sphere_solref : (ty == 1 ? m.sphere_box_solref : m.sphere_sphere_solref);
+        const float *solimp = ty == 0 ? m.plane_sphere_solimp : (ty == 1 ? m.sphere_box_solimp : m.sphere_sphere_solimp);
+        float kk, bb, imp;
+        kbi(solref, solimp, dt, bk, kk, bb, imp);
+        float Rr = fmaxf(invw * (1.f - imp) / imp, kMinVal);
+        s.mu = mu; s.D = 1.f / Rr; s.b = bb; s.kimp = kk * imp * bk; s.dist = bk;
+        s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2;
+      }
+      ncon = r + 1;
+    }
+  }
+  __syncwarp(qm);  // contact slots visible to the quad
+  int part[kMaxCon];
+  bool any_ss = false;
+  float knee_hits = 0.f, torso_hits = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxCon; c++) {
+    part[c] = 0;
+    if (c < ncon) {
+      const ContactSlot &s = es.con[c];
+      part[c] = participation(s, k);
+      any_ss |= (s.code1 >= 0 && s.code2 >= 0);
+      if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
+      if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
+    }
+  }
+
+  // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
+  const bool has_f = m.frictionloss_rows != 0;
+  Row rf[3], rl[3], rc[kMaxCon];
+  float fl[3], rff[3];   // friction loss and R*f per friction row
+  float lsign[3];        // limit row Jacobian entry (+-1, 0 when inactive)
+  float jq[kMaxCon][3];
+  contact_jv(es, ncon, part, cd, ba, bo, L.vb, L.vl, jq, qm);
+  const float esgn = (k & 1) ? -1.f : 1.f;  // pyramid edge of this lane: Jn + esgn*mu*Jt[k>>1]
+  const int et = 1 + (k >> 1);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const int d = 6 + 3 * k + j;
+    float kk, bb, imp;
+    fl[j] = (has_f && m.dof_frictionloss[d] > 0.f) ? m.dof_frictionloss[d] : 0.f;
+    kbi(m.dof_solref, m.dof_solimp, dt, 0.f, kk, bb, imp);
+    float Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
+    rf[j].D = 1.f / Rr;
+    rf[j].aref = -bb * L.vl[j];
+    rff[j] = fl[j] / rf[j].D;
+    float dlo = L.ql[j] - m.jnt_range[3 * k + j][0], dhi = m.jnt_range[3 * k + j][1] - L.ql[j];
+    float p = fminf(dlo, dhi);
+    bool act = p < 0.f;
+    lsign[j] = act ? (dlo < dhi ? 1.f : -1.f) : 0.f;
+    kbi(m.jnt_solref, m.jnt_solimp, dt, act ? p : 0.f, kk, bb, imp);
+    Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
+    rl[j].D = 1.f / Rr;
+    rl[j].aref = -bb * (lsign[j] * L.vl[j]) - kk * imp * (act ? p : 0.f);
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxCon; c++) {
+    if (c < ncon) {
+      const ContactSlot &s = es.con[c];
+      rc[c].D = s.D;
+      rc[c].aref = -s.b * (jq[c][0] + esgn * s.mu * jq[c][et]) - s.kimp;
+    }
+  }
+
+  // ---- unconstrained acceleration: M qacc_smooth = qfrc_smooth ---------------------------------------------
+  TreeMat F = M;
+  tree_factor(F, nullptr, qm);
+  float sb[6], sl[3];
+  tree_solve(F, fs_b, fs_l, sb, sl, qm);
+
+  // ---- Newton solver, one iteration (A.8) ------------------------------------------------------------------
+  // cost at the warm start and at qacc_smooth
+  float cost_w, cost_s, gauss_w;
+  float Maw_b[6], Maw_l[3], Mas_b[6], Mas_l[3];
+  float jaw_f[3], jaw_l[3], jaw_c[kMaxCon], jas_f[3], jas_l[3], jas_c[kMaxCon];
+  {
+    tree_matvec(M, L.wb, L.wl, Maw_b, Maw_l, qm);
+    tree_matvec(M, sb, sl, Mas_b, Mas_l, qm);
+    float jqw[kMaxCon][3], jqs[kMaxCon][3];
+    contact_jv(es, ncon, part, cd, ba, bo, L.wb, L.wl, jqw, qm);
+    contact_jv(es, ncon, part, cd, ba, bo, sb, sl, jqs, qm);
+    float cw = 0.f, cs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (fl[j] > 0.f) {
+        float xw = L.wl[j] - rf[j].aref, xs = sl[j] - rf[j].aref;
+        jaw_f[j] = xw; jas_f[j] = xs;
+        int zw = fzone(xw, rff[j]), zs = fzone(xs, rff[j]);
+        cw += zw == 1 ? 0.5f * rf[j].D * xw * xw : (zw == 2 ? fl[j] * (-0.5f * rff[j] - xw) : fl[j] * (-0.5f * rff[j] + xw));
+        cs += zs == 1 ? 0.5f * rf[j].D * xs * xs : (zs == 2 ? fl[j] * (-0.5f * rff[j] - xs) : fl[j] * (-0.5f * rff[j] + xs));
+      } else { jaw_f[j] = 0.f; jas_f[j] = 0.f; }
+      float xw = lsign[j] * L.wl[j] - rl[j].aref, xs = lsign[j] * sl[j] - rl[j].aref;
+      jaw_l[j] = xw; jas_l[j] = xs;
+      if (xw < 0.f) cw += 0.5f * rl[j].D * xw * xw;
+      if (xs < 0.f) cs += 0.5f * rl[j].D * xs * xs;
+    }
+#pragma unroll
+    for (int c = 0; c < kMaxCon; c++) {
+      if (c < ncon) {
+        float mu = es.con[c].mu;
+        float xw = jqw[c][0] + esgn * mu * jqw[c][et] - rc[c].aref, xs = jqs[c][0] + esgn * mu * jqs[c][et] - rc[c].aref;
+        jaw_c[c] = xw; jas_c[c] = xs;
+        if (xw < 0.f) cw += 0.5f * rc[c].D * xw * xw;
+        if (xs < 0.f) cs += 0.5f * rc[c].D * xs * xs;
+      }
+    }
+    // Gauss terms: leg part summed over the quad, base part replicated
+    float gw = 0.f, gs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) { gw = fmaf(Maw_l[j] - fs_l[j], L.wl[j] - sl[j], gw); }
+    gw = qsum(gw, qm);
+#pragma unroll
+    for (int d = 0; d < 6; d++) gw = fmaf(Maw_b[d] - fs_b[d], L.wb[d] - sb[d], gw);
+    (void)gs;
+    gauss_w = 0.5f * gw;
+    cost_w = qsum(cw, qm) + gauss_w;
+    cost_s = qsum(cs, qm);  // gauss(qacc_smooth) = 0
+  }
+  const bool use_w = cost_w < cost_s;
+  float xb[6], xl[3], Mab[6], Mal[3];  // qacc, M qacc
+  float gauss = use_w ? gauss_w : 0.f;
+#pragma unroll
+  for (int d = 0; d < 6; d++) { xb[d] = use_w ? L.wb[d] : sb[d]; Mab[d] = use_w ? Maw_b[d] : Mas_b[d]; }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    xl[j] = use_w ? L.wl[j] : sl[j]; Mal[j] = use_w ? Maw_l[j] : Mas_l[j];
+    rf[j].jaref = use_w ? jaw_f[j] : jas_f[j];
+    rl[j].jaref = use_w ? jaw_l[j] : jas_l[j];
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxCon; c++) if (c < ncon) rc[c].jaref = use_w ? jaw_c[c] : jas_c[c];
+
+  // forces, J^T f, gradient; Hessian additions
+  float gb[6], gl[3];
+  TreeMat H = M;
+  float Badd[21];
+#pragma unroll
+  for (int i = 0; i < 21; i++) Badd[i] = 0.f;
+  {
+    float qc_l[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      if (fl[j] > 0.f) {
+        int z = fzone(rf[j].jaref, rff[j]);
+        qc_l[j] += z == 1 ? -rf[j].D * rf[j].jaref : (z == 2 ? fl[j] : -fl[j]);
+        if (z == 1) H.D[tri(j, j)] += rf[j].D;
+      }
+      if (rl[j].jaref < 0.f) {
+        qc_l[j] += lsign[j] * (-rl[j].D * rl[j].jaref);
+        H.D[tri(j, j)] += rl[j].D * lsign[j] * lsign[j];
+      }
+    }
+    S6 S1 = S6{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, S2 = S1, Sb = S1;  // wrenches on link2 / link3 chains, base
+#pragma unroll
+    for (int c = 0; c < kMaxCon; c++) {
+      if (c < ncon) {
+        const ContactSlot &s = es.con[c];
+        float act = rc[c].jaref < 0.f ? 1.f : 0.f;
+        float fe = -rc[c].D * rc[c].jaref * act;  // force of this lane's pyramid edge
+        float de = rc[c].D * act;
+        float f0 = __shfl_sync(qm, fe, qbase + 0), f1 = __shfl_sync(qm, fe, qbase + 1), f2 = __shfl_sync(qm, fe, qbase + 2), f3 = __shfl_sync(qm, fe, qbase + 3);
+        float d0 = __shfl_sync(qm, de, qbase + 0), d1 = __shfl_sync(qm, de, qbase + 1), d2 = __shfl_sync(qm, de, qbase + 2), d3 = __shfl_sync(qm, de, qbase + 3);
+        // contact-frame force and world wrench about C
+        float Fn = (f0 + f1) + (f2 + f3), Ft1 = s.mu * (f0 - f1), Ft2 = s.mu * (f2 - f3);
+        V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
+                  s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
+        V3 r = V3{s.r[0], s.r[1], s.r[2]};
+        S6 w = S6{cross(r, g), g};
+        int dd1 = part[c] & 3, dd2 = (part[c] >> 2) & 3;
+        float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
+        S1 = fma6(s1w, w, S1);
+        S2 = fma6(s2w, w, S2);
+        float wb_ = (s.code2 >= 0 ? 1.f : 0.f) - (s.code1 >= 0 ? 1.f : 0.f);
+        Sb = fma6(wb_, w, Sb);
+        // Hessian: Jc^T W Jc with W from the 4 edge weights
+        float sd = (d0 + d1) + (d2 + d3);
+        if (sd > 0.f && !any_ss) {
+          int dep = dd2 ? dd2 : dd1;       // world-vs-leg contact: exactly one side is this leg (or none)
+          if (dep) {
+            float W00 = sd, W01 = s.mu * (d0 - d1), W02 = s.mu * (d2 - d3), W11 = s.mu * s.mu * (d0 + d1), W22 = s.mu * s.mu * (d2 + d3);
+            // columns of Jc for the 6 base dofs and the leg dofs (sign cancels in J^T W J)
+            float Jc[9][3], T[9][3];
+#pragma unroll
+            for (int d = 0; d < 9; d++) {
+              V3 col;
+              if (d < 3) col = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
+              else if (d < 6) col = bo[d - 3] + cross(ba[d - 3], r);
+              else col = (d - 6 <= dep) ? cd[d - 6].l + cross(cd[d - 6].a, r) : V3{0.f, 0.f, 0.f};
+              Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
+              Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
+              Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
+              T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
+              T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
+              T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++)
+#pragma unroll
+              for (int j = 0; j <= i; j++) Badd[tri(i, j)] += T[i][0] * Jc[j][0] + T[i][1] * Jc[j][1] + T[i][2] * Jc[j][2];
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int d = 0; d < 6; d++) H.C[j][d] += T[6 + j][0] * Jc[d][0] + T[6 + j][1] * Jc[d][1] + T[6 + j][2] * Jc[d][2];
+#pragma unroll
+              for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
+            }
+          }
+        }
+      }
+    }
+    // qfrc_constraint and gradient
+    gl[0] = Mal[0] - fs_l[0] - (qc_l[0] + dot6(cd[0], S1 + S2));
+    gl[1] = Mal[1] - fs_l[1] - (qc_l[1] + dot6(cd[1], S1 + S2));
+    gl[2] = Mal[2] - fs_l[2] - (qc_l[2] + dot6(cd[2], S2));
+    gb[0] = Mab[0] - fs_b[0] - Sb.l.x; gb[1] = Mab[1] - fs_b[1] - Sb.l.y; gb[2] = Mab[2] - fs_b[2] - Sb.l.z;
+#pragma unroll
+    for (int i = 0; i < 3; i++) gb[3 + i] = Mab[3 + i] - fs_b[3 + i] - (dot(ba[i], Sb.a) + dot(bo[i], Sb.l));
+  }
+
+  // Newton direction: search = -H^-1 grad
+  float hb[6], hl[3];
+  if (!any_ss) {
+    tree_factor(H, Badd, qm);
+    tree_solve(H, gb, gl, hb, hl, qm);
+  } else {
+    // ---- rare path: a leg-leg sphere contact couples two legs; gather to lane 0 and solve densely ----
+    float Hd[18 * 18], Ld[18 * 18], xd[18], yd[18];
+    float cdall[12][6];
+    for (int i = 0; i < 18 * 18; i++) Hd[i] = 0.f;
+    for (int kk = 0; kk < 4; kk++) {
+      for (int j = 0; j < 3; j++) {
+        float c6[6] = {cd[j].a.x, cd[j].a.y, cd[j].a.z, cd[j].l.x, cd[j].l.y, cd[j].l.z};
+        for (int i = 0; i < 6; i++) { float v = __shfl_sync(qm, c6[i], qbase + kk); cdall[3 * kk + j][i] = v; }
+        for (int d = 0; d < 6; d++) { float v = __shfl_sync(qm, H.C[j][d], qbase + kk); Hd[(6 + 3 * kk + j) * 18 + d] = v; Hd[d * 18 + 6 + 3 * kk + j] = v; }
+        for (int jj = 0; jj <= j; jj++) { float v = __shfl_sync(qm, H.D[tri(j, jj)], qbase + kk); Hd[(6 + 3 * kk + j) * 18 + 6 + 3 * kk + jj] = v; Hd[(6 + 3 * kk + jj) * 18 + 6 + 3 * kk + j] = v; }
+        float g = __shfl_sync(qm, gl[j], qbase + kk);
+        yd[6 + 3 * kk + j] = g;
+      }
+    }
+    for (int i = 0; i < 6; i++) { yd[i] = gb[i]; for (int j = 0; j <= i; j++) { Hd[i * 18 + j] = H.B[tri(i, j)]; Hd[j * 18 + i] = H.B[tri(i, j)]; } }
+    // edge weights of every contact (needed by lane 0)
+    float dall[kMaxCon][4];
+    for (int c = 0; c < kMaxCon; c++) {
+      float de = (c < ncon && rc[c].jaref < 0.f) ? rc[c].D : 0.f;
+      for (int e = 0; e < 4; e++) dall[c][e] = __shfl_sync(qm, de, qbase + e);
+    }
+    if (k == 0) {
+      for (int c = 0; c < ncon; c++) {
+        const ContactSlot &s = es.con[c];
+        V3 r = V3{s.r[0], s.r[1], s.r[2]};
+        float Jc[3][18];
+        for (int d = 0; d < 18; d++) {
+          V3 col = V3{0.f, 0.f, 0.f};
+          for (int side = 0; side < 2; side++) {
+            int code = side ? s.code2 : s.code1;
+            if (code < 0) continue;
+            float sg = side ? 1.f : -1.f;
+            int leg = code >> 2, dep = code & 3;
+            V3 cc = V3{0.f, 0.f, 0.f};
+            if (d < 3) cc = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
+            else if (d < 6) cc = bo[d - 3] + cross(ba[d - 3], r);
+            else if ((d - 6) / 3 == leg && (d - 6) % 3 <= dep) {
+              const float *q = cdall[d - 6];
+              cc = V3{q[3], q[4], q[5]} + cross(V3{q[0], q[1], q[2]}, r);
+            }
+            col = col + sg * cc;
+          }
+          for (int i = 0; i < 3; i++) Jc[i][d] = s.frame[3 * i] * col.x + s.frame[3 * i + 1] * col.y + s.frame[3 * i + 2] * col.z;
+        }
+        for (int e = 0; e < 4; e++) {
+          float de = dall[c][e];
+          if (de == 0.f) continue;
+          float sg = (e & 1) ? -s.mu : s.mu;
+          const float *Jt = Jc[1 + (e >> 1)];
+          for (int i = 0; i < 18; i++) {
+            float ji = (Jc[0][i] + sg * Jt[i]) * de;
+            if (ji == 0.f) continue;
+            for (int j = 0; j < 18; j++) Hd[i * 18 + j] += ji * (Jc[0][j] + sg * Jt[j]);
+          }
+        }
+      }
+      for (int i = 0; i < 18; i++)
+        for (int j = 0; j <= i; j++) {
+          float s = Hd[i * 18 + j];
+          for (int p = 0; p < j; p++) s -= Ld[i * 18 + p] * Ld[j * 18 + p];
+          Ld[i * 18 + j] = (i == j) ? sqrtf(s) : s / Ld[j * 18 + j];
+        }
+      for (int i = 0; i < 18; i++) {
+        float s = yd[i];
+        for (int p = 0; p < i; p++) s -= Ld[i * 18 + p] * xd[p];
+        xd[i] = s / Ld[i * 18 + i];
+      }
+      for (int i = 17; i >= 0; i--) {
+        float s = xd[i];
+        for (int p = i + 1; p < 18; p++) s -= Ld[p * 18 + i] * xd[p];
+        xd[i] = s / Ld[i * 18 + i];
+      }
+    }
+    for (int d = 0; d < 6; d++) hb[d] = __shfl_sync(qm, xd[d], qbase);
+    for (int kk = 0; kk < 4; kk++)
+      for (int j = 0; j < 3; j++) {
+        float v = __shfl_sync(qm, xd[6 + 3 * kk + j], qbase);
+        if (kk == k) hl[j] = v;
+      }
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) hb[d] = -hb[d];
+#pragma unroll
+  for (int j = 0; j < 3; j++) hl[j] = -hl[j];
+
+  // ---- line search along `search` (A.8.3) ---------------------------------------------------------------------
+  float alpha;
+  {
+    float mvb[6], mvl[3];
+    tree_matvec(M, hb, hl, mvb, mvl, qm);
+    float jqh[kMaxCon][3];
+    contact_jv(es, ncon, part, cd, ba, bo, hb, hl, jqh, qm);
+    float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];
+    float q1l = 0.f, q2l = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      q1l = fmaf(hl[j], Mal[j] - fs_l[j], q1l);
+      q2l = fmaf(hl[j], mvl[j], q2l);
+      rf[j].jv = hl[j];
+      rl[j].jv = lsign[j] * hl[j];
+    }
+    sn = qsum(sn, qm); q1l = qsum(q1l, qm); q2l = qsum(q2l, qm);
+#pragma unroll
+    for (int d = 0; d < 6; d++) { sn = fmaf(hb[d], hb[d], sn); q1l = fmaf(hb[d], Mab[d] - fs_b[d], q1l); q2l = fmaf(hb[d], mvb[d], q2l); }
+    const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
+    const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
+#pragma unroll
+    for (int c = 0; c < kMaxCon; c++) if (c < ncon) rc[c].jv = jqh[c][0] + esgn * es.con[c].mu * jqh[c][et];
+
+    // per-row quadratic coefficients (0.5 D Jaref^2, D jv Jaref, 0.5 D jv^2)
+    auto eval = [&](float a) -> LSPoint {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        if (fl[j] > 0.f) {
+          float ja = rf[j].jaref, jv = rf[j].jv, x = fmaf(a, jv, ja);
+          int z = fzone(x, rff[j]);
+          if (z == 1) { s0 += 0.5f * ja * ja * rf[j].D; s1 += jv * ja * rf[j].D; s2 += 0.5f * jv * jv * rf[j].D; }
+          else if (z == 2) { s0 += fl[j] * (-0.5f * rff[j] - ja); s1 += -fl[j] * jv; }
+          else { s0 += fl[j] * (-0.5f * rff[j] + ja); s1 += fl[j] * jv; }
+        }
+        {
+          float ja = rl[j].jaref, jv = rl[j].jv, x = fmaf(a, jv, ja);
+          if (x < 0.f) { s0 += 0.5f * ja * ja * rl[j].D; s1 += jv * ja * rl[j].D; s2 += 0.5f * jv * jv * rl[j].D; }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < kMaxCon; c++) {
+        if (c < ncon) {
+          float ja = rc[c].jaref, jv = rc[c].jv, x = fmaf(a, jv, ja);
+          if (x < 0.f) { s0 += 0.5f * ja * ja * rc[c].D; s1 += jv * ja * rc[c].D; s2 += 0.5f * jv * jv * rc[c].D; }
+        }
+      }
+      float t0 = gq0 + qsum(s0, qm), t1 = gq1 + qsum(s1, qm), t2 = gq2 + qsum(s2, qm);
+      LSPoint p;
+      p.alpha = a;
+      p.cost = a * a * t2 + a * t1 + t0;
+      p.d0 = 2.f * a * t2 + t1;
+      p.d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
+      return p;
+    };
+    LSPoint p0 = eval(0.f);
+    LSPoint lo = eval(p0.alpha - p0.d0 / p0.d1), hi;
+    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+    bool swap = true;
+    for (int it = 0; it < m.ls_iterations; it++) {
+      if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) break;
+      LSPoint lon = eval(lo.alpha - lo.d0 / lo.d1);
+      LSPoint hin = eval(hi.alpha - hi.d0 / hi.d1);
+      LSPoint mid = eval(0.5f * (lo.alpha + hi.alpha));
+      bool s1 = in_bracket(lo, lon); if (s1) lo = lon;
+      bool s2 = in_bracket(lo, mid); if (s2) lo = mid;
+      bool s3 = in_bracket(lo, hin); if (s3) lo = hin;
+      bool t1 = in_bracket(hi, hin); if (t1) hi = hin;
+      bool t2 = in_bracket(hi, mid); if (t2) hi = mid;
+      bool t3 = in_bracket(hi, lon); if (t3) hi = lon;
+      swap = s1 | s2 | s3 | t1 | t2 | t3;
+    }
+    bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+    alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+    if (!improved) alpha = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) ab[d] = fmaf(alpha, hb[d], xb[d]);
+#pragma unroll
+  for (int j = 0; j < 3; j++) al[j] = fmaf(alpha, hl[j], xl[j]);
+
+  if (want_stale) {
+    so.torso_pos = p1;
+    so.torso_rot = q1;
+    so.torso_ang = cvb.a;
+    so.torso_vel = cvb.l + cross(cvb.a, p1 - C);  // lin - off x ang
+    so.com = C;
+    so.foot_site = pos[2] + rotate(V3{m.site_pos[1 + k][0], m.site_pos[1 + k][1], m.site_pos[1 + k][2]}, rot[2]);
+    so.lower_pos = pos[2];
+    so.lower_ang = cv[2].a;
+    so.lower_vel = cv[2].l + cross(cv[2].a, pos[2] - C);
+#pragma unroll
+    for (int j = 0; j < 3; j++) so.frc[j] = frc[j];
+    so.knee_hits = knee_hits;
+    so.torso_hits = torso_hits;
+    if (DBG && dbg) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        dbg->pos[j] = pos[j]; dbg->rot[j] = rot[j]; dbg->ang[j] = cv[j].a; dbg->vel[j] = cv[j].l + cross(cv[j].a, pos[j] - C);
+        dbg->qacc_l[j] = al[j];
+      }
+#pragma unroll
+      for (int d = 0; d < 6; d++) dbg->qacc_b[d] = ab[d];
+    }
+  }
+  es.ncon = ncon;
+}
+
+}  // namespace pupper

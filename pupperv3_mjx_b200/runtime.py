@@ -1,0 +1,260 @@
+"""Device runtime: owns the SoA state tensors and calls the C ABI of ``libpupper_env.so``.
+
+torch is plumbing here (device memory + streams); the product is the CUDA library.  There is no CPU
+fallback: constructing an ``EnvRuntime`` without the built library or without a CUDA device raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import abi
+from .system import System
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpupper_env.so")
+_lib: Optional[C.CDLL] = None
+
+
+class PupperError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library() -> C.CDLL:
+    """Load the C-ABI library (no GPU needed just to load it and inspect symbols)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise PupperError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`"
+                              " (there is no CPU fallback)")
+        lib = C.CDLL(_LIB_PATH)
+        lib.pupper_strerror.restype = C.c_char_p
+        lib.pupper_last_cuda_error.restype = C.c_char_p
+        lib.pupper_model_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        lib.pupper_model_destroy.argtypes = [C.c_void_p]
+        lib.pupper_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_last_launch_count.argtypes = [C.c_void_p]
+        lib.pupper_state_rows.argtypes = [C.c_void_p, C.c_void_p]
+        for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut,
+                               abi.PupperEpisode)):
+            if lib.pupper_sizeof(i) != C.sizeof(s):
+                raise PupperError(f"ABI struct {s.__name__}: library {lib.pupper_sizeof(i)} B vs ctypes {C.sizeof(s)} B")
+        if lib.pupper_abi_version() != abi.ABI_VERSION:
+            raise PupperError("ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def _check(lib, rc: int, what: str):
+    if rc != 0:
+        msg = lib.pupper_strerror(rc).decode()
+        if rc == -3:
+            msg += ": " + lib.pupper_last_cuda_error().decode()
+        raise PupperError(f"{what} failed ({rc}): {msg}")
+
+
+class PipelineStateView:
+    """Opaque handle standing in for Brax's ``pipeline_state``; materialises env-major fields on request."""
+
+    def __init__(self, runtime: "EnvRuntime"):
+        self.runtime = runtime
+
+    @property
+    def q(self) -> torch.Tensor:
+        return self.runtime.field("qpos").t()
+
+    qpos = q
+
+    @property
+    def qd(self) -> torch.Tensor:
+        return self.runtime.field("qvel").t()
+
+    qvel = qd
+
+    @property
+    def qacc_warmstart(self) -> torch.Tensor:
+        return self.runtime.field("qacc_warmstart").t()
+
+    @property
+    def sensordata(self):
+        raise NotImplementedError("sensors are never read by the env (SURVEY.md P11) and are not computed")
+
+
+class EnvRuntime:
+    def __init__(self, model_desc: abi.PupperModelDesc, env_cfg: abi.PupperEnvCfg, n_envs: int, device: int = 0,
+                 episode: bool = False, debug: bool = False):
+        if not torch.cuda.is_available():
+            raise PupperError("no CUDA device: the B200 kernel is the only implementation (no CPU fallback)")
+        self.lib = load_library()
+        self.n_envs = int(n_envs)
+        self.device = torch.device("cuda", device)
+        self.device_index = device
+        self.cfg = env_cfg
+        self.stride = (self.n_envs + 31) // 32 * 32
+        self._model = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.pupper_model_create(C.byref(model_desc), C.byref(env_cfg), device, C.byref(self._model)),
+                   "pupper_model_create")
+        rows = (C.c_int32 * 14)()
+        _check(self.lib, self.lib.pupper_state_rows(C.byref(env_cfg), rows), "pupper_state_rows")
+        self._fields: Dict[str, torch.Tensor] = {}
+        self.state = abi.PupperState()
+        self.state.stride = self.stride
+        for name, r in zip(abi.STATE_FIELDS, rows):
+            dt = torch.int32 if name in abi.STATE_INT_FIELDS else torch.float32
+            t = torch.zeros((r, self.stride), dtype=dt, device=self.device)
+            self._fields[name] = t
+            setattr(self.state, name, t.data_ptr())
+        H = env_cfg.observation_history
+        self.obs = torch.zeros((self.n_envs, H * abi.OBS_DIM), dtype=torch.float32, device=self.device)
+        self.state.obs = self.obs.data_ptr()
+        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+        self.done = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+        self.metrics = torch.zeros((self.n_envs, abi.NMETRIC), dtype=torch.float32, device=self.device)
+        self.out = abi.PupperStepOut()
+        self.out.reward, self.out.done, self.out.metrics = self.reward.data_ptr(), self.done.data_ptr(), self.metrics.data_ptr()
+        self.dbg: Dict[str, torch.Tensor] = {}
+        if debug:
+            mc = model_desc.max_contact_points
+            shapes = {"dbg_x_pos": (13, 3), "dbg_x_rot": (13, 4), "dbg_xd_vel": (13, 3), "dbg_xd_ang": (13, 3),
+                      "dbg_qfrc_actuator": (18,), "dbg_contact_dist": (mc,), "dbg_contact_geom": (mc, 2),
+                      "dbg_site_xpos": (5, 3), "dbg_qacc": (18,)}
+            for name, shp in shapes.items():
+                dt = torch.int32 if name == "dbg_contact_geom" else torch.float32
+                t = torch.zeros((self.n_envs,) + shp, dtype=dt, device=self.device)
+                self.dbg[name] = t
+                setattr(self.out, name, t.data_ptr())
+        self._dr_struct: Optional[abi.PupperDR] = None
+        self._dr_tensors: Dict[str, torch.Tensor] = {}
+        self.episode: Optional[abi.PupperEpisode] = None
+        self._ep_tensors: Dict[str, torch.Tensor] = {}
+        if episode:
+            self._alloc_episode()
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_model", None) and self._model.value:
+                self.lib.pupper_model_destroy(self._model)
+                self._model = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- allocation helpers -----------------------------------------------------------------------
+    def _alloc_episode(self):
+        ep = abi.PupperEpisode()
+        ep.stride = self.stride
+        for name, r in abi.EPISODE_ROWS.items():
+            dt = torch.int32 if name == "steps" else torch.float32
+            t = torch.zeros((r, self.stride), dtype=dt, device=self.device)
+            self._ep_tensors[name] = t
+            setattr(ep, name, t.data_ptr())
+        H = self.cfg.observation_history
+        self._ep_tensors["first_obs"] = torch.zeros((self.n_envs, H * abi.OBS_DIM), dtype=torch.float32, device=self.device)
+        ep.first_obs = self._ep_tensors["first_obs"].data_ptr()
+        self._ep_tensors["totals"] = torch.zeros(abi.N_TOTALS, dtype=torch.float32, device=self.device)
+        ep.totals = self._ep_tensors["totals"].data_ptr()
+        self.episode = ep
+
+    def set_dr(self, sys_v: Optional[System]):
+        """Stage the batched DR leaves (domain_randomize output) on the device as SoA."""
+        if sys_v is None or not sys_v.is_batched():
+            self._dr_struct, self._dr_tensors = None, {}
+            return
+        B = sys_v.body_mass.shape[0]
+        if B != self.n_envs:
+            raise PupperError(f"domain-randomised system has {B} envs, runtime has {self.n_envs}")
+        host = {
+            "friction": sys_v.geom_friction[:, 0, 0][None],
+            "kp": sys_v.actuator_gainprm[:, 0, 0][None],
+            "kd": -sys_v.actuator_biasprm[:, 0, 2][None],
+            "base_ipos": sys_v.body_ipos[:, 1].T,
+            "body_inertia": sys_v.body_inertia[:, 1:].reshape(B, 39).T,
+            "body_mass": sys_v.body_mass[:, 1:].T,
+        }
+        dr = abi.PupperDR()
+        dr.stride = self.stride
+        for name, a in host.items():
+            t = torch.zeros((abi.DR_ROWS[name], self.stride), dtype=torch.float32, device=self.device)
+            t[:, :B] = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(self.device)
+            self._dr_tensors[name] = t
+            setattr(dr, name, t.data_ptr())
+        self._dr_struct = dr
+
+    # ---- hot path -----------------------------------------------------------------------------------------
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset(self, keys: torch.Tensor):
+        keys = keys.to(device=self.device).contiguous()
+        if keys.dtype not in (torch.int32, torch.uint32) or keys.numel() != 2 * self.n_envs:
+            raise PupperError("keys must be a 32-bit integer tensor of shape [n_envs, 2]")
+        self._keys = keys
+        with torch.cuda.device(self.device):
+            rc = self.lib.pupper_reset(self._model, self.n_envs, keys.data_ptr(),
+                                       C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
+                                       C.byref(self.out), C.byref(self.episode) if self.episode else None, self._stream())
+        _check(self.lib, rc, "pupper_reset")
+        self.launches += self.lib.pupper_last_launch_count(self._model)
+
+    def step(self, action: torch.Tensor):
+        if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
+                or action.numel() != self.n_envs * abi.NU:
+            raise PupperError("action must be a contiguous float32 CUDA tensor of shape [n_envs, 12] on the env's device")
+        with torch.cuda.device(self.device):
+            rc = self.lib.pupper_step(self._model, self.n_envs, C.byref(self._dr_struct) if self._dr_struct else None,
+                                      C.byref(self.state), action.data_ptr(), C.byref(self.out),
+                                      C.byref(self.episode) if self.episode else None, self._stream())
+        _check(self.lib, rc, "pupper_step")
+        self.launches += 1
+
+    # ---- views -------------------------------------------------------------------------------------------------
+    def field(self, name: str) -> torch.Tensor:
+        """SoA field ``[rows, n_envs]`` (a view without the stride padding)."""
+        return self._fields[name][:, : self.n_envs]
+
+    def episode_field(self, name: str) -> torch.Tensor:
+        t = self._ep_tensors[name]
+        return t if name in ("first_obs", "totals") else t[:, : self.n_envs]
+
+    def pipeline_state(self) -> PipelineStateView:
+        return PipelineStateView(self)
+
+    def info(self) -> Dict[str, object]:
+        """Env-major views of the reference's ``state.info`` entries (environment.py:321-334)."""
+        n, f = self.n_envs, self.field
+        La, Li = self.cfg.n_latency, self.cfg.n_imu_latency
+        bits = f("last_contact")[0]
+        info = {
+            "rng": f("rng").t(),
+            "last_act": f("last_act").t(),
+            "action_buffer": f("action_buffer").t().reshape(n, abi.NU, La),
+            "imu_buffer": f("imu_buffer").t().reshape(n, 6, Li),
+            "last_vel": f("last_vel").t(),
+            "command": f("command").t(),
+            "last_contact": torch.stack([(bits >> i) & 1 for i in range(4)], dim=1).bool(),
+            "feet_air_time": f("feet_air_time").t(),
+            "rewards": {name: self.metrics[:, 1 + i] for i, name in enumerate(abi.REWARD_NAMES)},
+            "kick": f("kick").t(),
+            "step": f("step")[0],
+            "desired_world_z_in_body_frame": f("desired_world_z").t(),
+        }
+        if self.episode is not None:
+            ef = self.episode_field
+            info.update({
+                "steps": ef("steps")[0], "truncation": ef("truncation")[0], "episode_done": ef("episode_done")[0],
+                "episode_metrics": dict(
+                    sum_reward=ef("sum_reward")[0], length=ef("length")[0],
+                    **{name: ef("sum_metrics")[i] for i, name in enumerate(abi.METRIC_NAMES)}),
+                "first_obs": ef("first_obs"),
+            })
+        return info
