@@ -63,7 +63,7 @@ struct ObsCtx {
 // _get_obs (environment.py:485-543). `rng` is info["rng"] on entry; returns the new info["rng"].
 // Updates the IMU buffer and the observation history in global memory.
 __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p, int e, int k, unsigned qm, int qbase, uint2 rng,
-                                         const StaleOut &so, const ObsCtx &oc, bool zero_history) {
+                                         const StaleOut &so, const ObsCtx &oc, bool zero_history, bool valid) {
   const PupperEnvCfg &c = sh.c;
   const int stride = p.st.stride;
   // split(rng, 6): lane 0 -> new rng, lane 1 -> ang key, lane 2 -> gravity key, lane 3 -> imu sample key
@@ -102,7 +102,7 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
       for (int l = 0; l < Li; l++) {
         float *ptr = p.st.imu_buffer + (size_t)(row * Li + l) * stride + e;
         float old = zero_history ? (row == 5 ? -1.f : 0.f) : *ptr;
-        *ptr = prev;
+        if (valid) *ptr = prev;
         if (l == imu_idx) lag = prev;
         prev = old;
       }
@@ -114,33 +114,34 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
   const int H = c.observation_history;
   float *obs = p.st.obs + (size_t)e * H * PUPPER_OBS_DIM;
   for (int h = H - 1; h >= 1; h--)
-    for (int i = k; i < PUPPER_OBS_DIM; i += 4) obs[h * PUPPER_OBS_DIM + i] = zero_history ? 0.f : obs[(h - 1) * PUPPER_OBS_DIM + i];
+    for (int i = k; i < PUPPER_OBS_DIM; i += 4) if (valid) obs[h * PUPPER_OBS_DIM + i] = zero_history ? 0.f : obs[(h - 1) * PUPPER_OBS_DIM + i];
   __syncwarp(qm);
   auto clip100 = [](float x) { return fminf(fmaxf(x, -100.f), 100.f); };
   // entries 0..11: imu(6), command(3), desired_z(3); this lane writes i = k, k+4, k+8
   {
-    obs[k] = clip100(lag_imu[0]);
+    if (valid) obs[k] = clip100(lag_imu[0]);
     int i1 = k + 4;
     float v1 = i1 < 6 ? lag_imu[1] : (i1 == 6 ? oc.command[0] : oc.command[1]);
-    obs[i1] = clip100(v1);
+    if (valid) obs[i1] = clip100(v1);
     int i2 = k + 8;
     float v2 = i2 == 8 ? oc.command[2] : (i2 == 9 ? oc.desired_z[0] : (i2 == 10 ? oc.desired_z[1] : oc.desired_z[2]));
-    obs[i2] = clip100(v2);
+    if (valid) obs[i2] = clip100(v2);
   }
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const int u = 3 * k + j;
     float mn = __fmul_rn(uniform(k_motor, (uint32_t)u, -1.f, 1.f), c.motor_angle_noise);
     float ln = __fmul_rn(uniform(k_act, (uint32_t)u, -1.f, 1.f), c.last_action_noise);
-    obs[12 + u] = clip100(oc.ql[j] - c.default_pose[u] + mn);
-    obs[24 + u] = clip100(oc.last_act[j] + ln);
+    if (valid) obs[12 + u] = clip100(oc.ql[j] - c.default_pose[u] + mn);
+    if (valid) obs[24 + u] = clip100(oc.last_act[j] + ln);
   }
   return new_rng;
 }
 
 template <bool RESET, bool DBG>
 __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
-  __shared__ BlockShared sh;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.model);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.m);
@@ -148,13 +149,18 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
     src = reinterpret_cast<const uint32_t *>(p.cfg);
     dst = reinterpret_cast<uint32_t *>(&sh.c);
     for (int i = threadIdx.x; i < (int)(sizeof(PupperEnvCfg) / 4); i += kBlock) dst[i] = src[i];
+    src = reinterpret_cast<const uint32_t *>(p.derived);
+    dst = reinterpret_cast<uint32_t *>(&sh.d);
+    for (int i = threadIdx.x; i < (int)(sizeof(DerivedConsts) / 4); i += kBlock) dst[i] = src[i];
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, k = threadIdx.x & 3;
   const int el = threadIdx.x >> 2;
-  const int e = blockIdx.x * kEnvsPerBlock + el;
-  if (e >= p.n_envs) return;
-  const unsigned qm = 0xFu << (lane & 28);
+  // Every shuffle uses the full warp mask, so all 32 lanes stay convergent: quads past the end of the
+  // batch recompute the last env (identical values) and their lanes write nothing different.
+  const bool valid = blockIdx.x * kEnvsPerBlock + el < p.n_envs;
+  const int e = min(blockIdx.x * kEnvsPerBlock + el, p.n_envs - 1);
+  const unsigned qm = 0xffffffffu;
   const int qbase = lane & 28;
   const PupperModelDesc &m = sh.m;
   const PupperEnvCfg &c = sh.c;
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
     for (int j = 0; j < 3; j++) { L.ql[j] = c.init_q[7 + 3 * k + j]; L.vl[j] = 0.f; L.wl[j] = 0.f; L.ctrl[j] = 0.f; }
 #pragma unroll
     for (int d = 0; d < 6; d++) { L.vb[d] = 0.f; L.wb[d] = 0.f; }
-    forward<DBG>(sh, es, L, k, qm, qbase, ab, al, true, so, &dbg);  // pipeline_init = make_data + forward
+    forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, true, so, &dbg);  // pipeline_init = make_data + forward
 #pragma unroll
     for (int d = 0; d < 6; d++) L.wb[d] = ab[d];
 #pragma unroll
@@ -227,22 +233,22 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
     for (int i = 0; i < 3; i++) { oc.command[i] = __shfl_sync(qm, cmd[i], qbase); oc.desired_z[i] = __shfl_sync(qm, dz[i], qbase); }
 #pragma unroll
     for (int j = 0; j < 3; j++) { oc.last_act[j] = 0.f; oc.ql[j] = L.ql[j]; }
-    rng = get_obs(sh, p, e, k, qm, qbase, k_rng, so, oc, true);
+    rng = get_obs(sh, p, e, k, qm, qbase, k_rng, so, oc, true, valid);
     // info / state
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const int u = 3 * k + j;
-      p.st.last_act[(size_t)u * stride + e] = 0.f;
-      p.st.last_vel[(size_t)u * stride + e] = 0.f;
-      for (int l = 0; l < c.n_latency; l++) p.st.action_buffer[(size_t)(u * c.n_latency + l) * stride + e] = 0.f;
+      if (valid) p.st.last_act[(size_t)u * stride + e] = 0.f;
+      if (valid) p.st.last_vel[(size_t)u * stride + e] = 0.f;
+      for (int l = 0; l < c.n_latency; l++) if (valid) p.st.action_buffer[(size_t)(u * c.n_latency + l) * stride + e] = 0.f;
     }
-    p.st.feet_air_time[(size_t)k * stride + e] = 0.f;
+    if (valid) p.st.feet_air_time[(size_t)k * stride + e] = 0.f;
     if (k == 0) {
-      p.st.last_contact[e] = 0u; p.st.step[e] = 0;
-      p.st.kick[e] = 0.f; p.st.kick[stride + e] = 0.f;
-      p.out.reward[e] = 0.f; p.out.done[e] = 0.f;
+      if (valid) p.st.last_contact[e] = 0u; if (valid) p.st.step[e] = 0;
+      if (valid) p.st.kick[e] = 0.f; if (valid) p.st.kick[stride + e] = 0.f;
+      if (valid) p.out.reward[e] = 0.f; if (valid) p.out.done[e] = 0.f;
     }
-    for (int i = k; i < PUPPER_NMETRIC; i += 4) p.out.metrics[(size_t)e * PUPPER_NMETRIC + i] = 0.f;
+    for (int i = k; i < PUPPER_NMETRIC; i += 4) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + i] = 0.f;
   } else {
     // ---- step (environment.py:348-483) ---------------------------------------------------------------------
     rng = make_uint2(p.st.rng[e], p.st.rng[stride + e]);
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
       for (int l = 0; l < La; l++) {
         float *ptr = p.st.action_buffer + (size_t)(u_ * La + l) * stride + e;
         float old = *ptr;
-        *ptr = prev;
+        if (valid) *ptr = prev;
         if (l == aidx) lag = prev;
         prev = old;
       }
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
     // S5 physics: n_frames x (forward ; semi-implicit Euler)
     const float dt = m.timestep;
     for (int f = 0; f < c.n_frames; f++) {
-      forward<DBG>(sh, es, L, k, qm, qbase, ab, al, f == c.n_frames - 1, so, &dbg);
+      forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, f == c.n_frames - 1, so, &dbg);
 #pragma unroll
       for (int d = 0; d < 6; d++) { L.wb[d] = ab[d]; L.vb[d] = fmaf(ab[d], dt, L.vb[d]); }
 #pragma unroll
@@ -319,81 +325,81 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
 #pragma unroll
     for (int j = 0; j < 3; j++) oc.ql[j] = L.ql[j];
     // S6 observation (reads the not-yet-updated last_act / command / desired_z)
-    rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false);
+    rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false, valid);
   }
 
   // ---- write back the physics state -------------------------------------------------------------------------
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const int u = 3 * k + j;
-    p.st.qpos[(size_t)(7 + u) * stride + e] = L.ql[j];
-    p.st.qvel[(size_t)(6 + u) * stride + e] = L.vl[j];
-    p.st.qacc_warmstart[(size_t)(6 + u) * stride + e] = L.wl[j];
+    if (valid) p.st.qpos[(size_t)(7 + u) * stride + e] = L.ql[j];
+    if (valid) p.st.qvel[(size_t)(6 + u) * stride + e] = L.vl[j];
+    if (valid) p.st.qacc_warmstart[(size_t)(6 + u) * stride + e] = L.wl[j];
   }
   for (int i = k; i < 7; i += 4) {
     float v = 0.f;
 #pragma unroll
     for (int t = 0; t < 7; t++) if (t == i) v = L.qb[t];
-    p.st.qpos[(size_t)i * stride + e] = v;
+    if (valid) p.st.qpos[(size_t)i * stride + e] = v;
   }
   for (int i = k; i < 6; i += 4) {
     float v = 0.f, w = 0.f;
 #pragma unroll
     for (int t = 0; t < 6; t++) if (t == i) { v = L.vb[t]; w = L.wb[t]; }
-    p.st.qvel[(size_t)i * stride + e] = v;
-    p.st.qacc_warmstart[(size_t)i * stride + e] = w;
+    if (valid) p.st.qvel[(size_t)i * stride + e] = v;
+    if (valid) p.st.qacc_warmstart[(size_t)i * stride + e] = w;
   }
-  if (k == 0) { p.st.rng[e] = rng.x; p.st.rng[stride + e] = rng.y; }
+  if (k == 0) { if (valid) p.st.rng[e] = rng.x; if (valid) p.st.rng[stride + e] = rng.y; }
 
   if (DBG) {
     if (p.out.dbg_x_pos) {
       float *xp = p.out.dbg_x_pos + (size_t)e * 39, *xr = p.out.dbg_x_rot + (size_t)e * 52;
       float *xv = p.out.dbg_xd_vel + (size_t)e * 39, *xa = p.out.dbg_xd_ang + (size_t)e * 39;
       if (k == 0) {
-        xp[0] = so.torso_pos.x; xp[1] = so.torso_pos.y; xp[2] = so.torso_pos.z;
-        xr[0] = so.torso_rot.w; xr[1] = so.torso_rot.x; xr[2] = so.torso_rot.y; xr[3] = so.torso_rot.z;
-        xv[0] = so.torso_vel.x; xv[1] = so.torso_vel.y; xv[2] = so.torso_vel.z;
-        xa[0] = so.torso_ang.x; xa[1] = so.torso_ang.y; xa[2] = so.torso_ang.z;
+        if (valid) xp[0] = so.torso_pos.x; if (valid) xp[1] = so.torso_pos.y; if (valid) xp[2] = so.torso_pos.z;
+        if (valid) xr[0] = so.torso_rot.w; if (valid) xr[1] = so.torso_rot.x; if (valid) xr[2] = so.torso_rot.y; if (valid) xr[3] = so.torso_rot.z;
+        if (valid) xv[0] = so.torso_vel.x; if (valid) xv[1] = so.torso_vel.y; if (valid) xv[2] = so.torso_vel.z;
+        if (valid) xa[0] = so.torso_ang.x; if (valid) xa[1] = so.torso_ang.y; if (valid) xa[2] = so.torso_ang.z;
       }
       for (int j = 0; j < 3; j++) {
         int b = 1 + 3 * k + j;
-        xp[3 * b] = dbg.pos[j].x; xp[3 * b + 1] = dbg.pos[j].y; xp[3 * b + 2] = dbg.pos[j].z;
-        xr[4 * b] = dbg.rot[j].w; xr[4 * b + 1] = dbg.rot[j].x; xr[4 * b + 2] = dbg.rot[j].y; xr[4 * b + 3] = dbg.rot[j].z;
-        xv[3 * b] = dbg.vel[j].x; xv[3 * b + 1] = dbg.vel[j].y; xv[3 * b + 2] = dbg.vel[j].z;
-        xa[3 * b] = dbg.ang[j].x; xa[3 * b + 1] = dbg.ang[j].y; xa[3 * b + 2] = dbg.ang[j].z;
+        if (valid) xp[3 * b] = dbg.pos[j].x; if (valid) xp[3 * b + 1] = dbg.pos[j].y; if (valid) xp[3 * b + 2] = dbg.pos[j].z;
+        if (valid) xr[4 * b] = dbg.rot[j].w; if (valid) xr[4 * b + 1] = dbg.rot[j].x; if (valid) xr[4 * b + 2] = dbg.rot[j].y; if (valid) xr[4 * b + 3] = dbg.rot[j].z;
+        if (valid) xv[3 * b] = dbg.vel[j].x; if (valid) xv[3 * b + 1] = dbg.vel[j].y; if (valid) xv[3 * b + 2] = dbg.vel[j].z;
+        if (valid) xa[3 * b] = dbg.ang[j].x; if (valid) xa[3 * b + 1] = dbg.ang[j].y; if (valid) xa[3 * b + 2] = dbg.ang[j].z;
       }
     }
     if (p.out.dbg_qfrc_actuator) {
       float *o = p.out.dbg_qfrc_actuator + (size_t)e * 18;
-      for (int j = 0; j < 3; j++) o[6 + 3 * k + j] = so.frc[j];
-      if (k == 0) for (int d = 0; d < 6; d++) o[d] = 0.f;
+      for (int j = 0; j < 3; j++) if (valid) o[6 + 3 * k + j] = so.frc[j];
+      if (k == 0) for (int d = 0; d < 6; d++) if (valid) o[d] = 0.f;
     }
     if (p.out.dbg_qacc) {
       float *o = p.out.dbg_qacc + (size_t)e * 18;
-      for (int j = 0; j < 3; j++) o[6 + 3 * k + j] = dbg.qacc_l[j];
-      if (k == 0) for (int d = 0; d < 6; d++) o[d] = dbg.qacc_b[d];
+      for (int j = 0; j < 3; j++) if (valid) o[6 + 3 * k + j] = dbg.qacc_l[j];
+      if (k == 0) for (int d = 0; d < 6; d++) if (valid) o[d] = dbg.qacc_b[d];
     }
     if (p.out.dbg_site_xpos) {
       float *o = p.out.dbg_site_xpos + (size_t)e * 15;
-      o[3 + 3 * k] = so.foot_site.x; o[4 + 3 * k] = so.foot_site.y; o[5 + 3 * k] = so.foot_site.z;
+      if (valid) o[3 + 3 * k] = so.foot_site.x; if (valid) o[4 + 3 * k] = so.foot_site.y; if (valid) o[5 + 3 * k] = so.foot_site.z;
       if (k == 0) {
         V3 s = so.torso_pos + rotate(V3{m.site_pos[0][0], m.site_pos[0][1], m.site_pos[0][2]}, so.torso_rot);
-        o[0] = s.x; o[1] = s.y; o[2] = s.z;
+        if (valid) o[0] = s.x; if (valid) o[1] = s.y; if (valid) o[2] = s.z;
       }
     }
     if (p.out.dbg_contact_dist && k == 0) {
       const int mc = m.max_contact_points;
       for (int i = 0; i < mc; i++) {
         bool on = i < es.ncon;
-        p.out.dbg_contact_dist[(size_t)e * mc + i] = on ? es.con[i].dist : 1.0f;
+        if (valid) p.out.dbg_contact_dist[(size_t)e * mc + i] = on ? es.con[i].dist : 1.0f;
         int g1 = -1, g2 = -1;
         if (on) {
           const ContactSlot &s = es.con[i];
           g1 = s.s1 >= 0 ? m.sphere_geomid[s.s1] : m.floor_geomid;
           g2 = s.s2 >= 0 ? m.sphere_geomid[s.s2] : -2;  // -2: a world box (id not tracked)
         }
-        p.out.dbg_contact_geom[((size_t)e * mc + i) * 2] = g1;
-        p.out.dbg_contact_geom[((size_t)e * mc + i) * 2 + 1] = g2;
+        if (valid) p.out.dbg_contact_geom[((size_t)e * mc + i) * 2] = g1;
+        if (valid) p.out.dbg_contact_geom[((size_t)e * mc + i) * 2 + 1] = g2;
       }
     }
   }
@@ -401,18 +407,18 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
   if (RESET) {
     // persistent info written by reset; fused wrapper state
 #pragma unroll
-    for (int i = 0; i < 3; i++) if (k == i) { p.st.command[(size_t)i * stride + e] = oc.command[i]; p.st.desired_world_z[(size_t)i * stride + e] = oc.desired_z[i]; }
+    for (int i = 0; i < 3; i++) if (k == i) { if (valid) p.st.command[(size_t)i * stride + e] = oc.command[i]; if (valid) p.st.desired_world_z[(size_t)i * stride + e] = oc.desired_z[i]; }
     if (p.has_ep) {
       const int es_ = p.ep.stride;
       __syncwarp(qm);
-      for (int i = k; i < PUPPER_NQ; i += 4) p.ep.first_qpos[(size_t)i * es_ + e] = p.st.qpos[(size_t)i * stride + e];
+      for (int i = k; i < PUPPER_NQ; i += 4) if (valid) p.ep.first_qpos[(size_t)i * es_ + e] = p.st.qpos[(size_t)i * stride + e];
       for (int i = k; i < PUPPER_NV; i += 4) {
-        p.ep.first_qvel[(size_t)i * es_ + e] = p.st.qvel[(size_t)i * stride + e];
-        p.ep.first_warmstart[(size_t)i * es_ + e] = p.st.qacc_warmstart[(size_t)i * stride + e];
+        if (valid) p.ep.first_qvel[(size_t)i * es_ + e] = p.st.qvel[(size_t)i * stride + e];
+        if (valid) p.ep.first_warmstart[(size_t)i * es_ + e] = p.st.qacc_warmstart[(size_t)i * stride + e];
       }
-      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i];
-      for (int i = k; i < PUPPER_NMETRIC; i += 4) p.ep.sum_metrics[(size_t)i * es_ + e] = 0.f;
-      if (k == 0) { p.ep.steps[e] = 0; p.ep.truncation[e] = 0.f; p.ep.sum_reward[e] = 0.f; p.ep.length[e] = 0.f; p.ep.episode_done[e] = 0.f; }
+      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) if (valid) p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i];
+      for (int i = k; i < PUPPER_NMETRIC; i += 4) if (valid) p.ep.sum_metrics[(size_t)i * es_ + e] = 0.f;
+      if (k == 0) { if (valid) p.ep.steps[e] = 0; if (valid) p.ep.truncation[e] = 0.f; if (valid) p.ep.sum_reward[e] = 0.f; if (valid) p.ep.length[e] = 0.f; if (valid) p.ep.episode_done[e] = 0.f; }
     }
     return;
   }
@@ -435,7 +441,7 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 3; j++) bad |= (L.ql[j] < c.joint_lower[3 * k + j]) || (L.ql[j] > c.joint_upper[3 * k + j]);
-  bool done = (__ballot_sync(qm, bad) & qm) != 0u;
+  bool done = ((__ballot_sync(qm, bad) >> qbase) & 0xFu) != 0u;
   done |= rup.z < c.cos_terminal_body_angle;
   done |= so.torso_pos.z < c.terminal_body_z;
   const int step0 = p.st.step[e];
@@ -503,27 +509,27 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const int u = 3 * k + j;
-    p.st.last_act[(size_t)u * stride + e] = act[j];
-    p.st.last_vel[(size_t)u * stride + e] = L.vl[j];
+    if (valid) p.st.last_act[(size_t)u * stride + e] = act[j];
+    if (valid) p.st.last_vel[(size_t)u * stride + e] = L.vl[j];
   }
-  p.st.feet_air_time[(size_t)k * stride + e] = filt_mm ? 0.f : air;
+  if (valid) p.st.feet_air_time[(size_t)k * stride + e] = filt_mm ? 0.f : air;
   const uint32_t cbits = (__ballot_sync(qm, contact) >> qbase) & 0xFu;
   int step = step0 + 1;
   const bool resample = step > c.resample_velocity_step;
-  if (resample) {
+  if (__any_sync(qm, resample)) {
     float cmd[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
-    if (k == 0) { sample_command(c, cmd_rng, cmd); sample_body_orientation(c, cmd_rng, dz); }
+    if (k == 0 && resample) { sample_command(c, cmd_rng, cmd); sample_body_orientation(c, cmd_rng, dz); }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       float cv = __shfl_sync(qm, cmd[i], qbase), dv = __shfl_sync(qm, dz[i], qbase);
-      if (k == i) { p.st.command[(size_t)i * stride + e] = cv; p.st.desired_world_z[(size_t)i * stride + e] = dv; }
+      if (k == i && resample) { if (valid) p.st.command[(size_t)i * stride + e] = cv; if (valid) p.st.desired_world_z[(size_t)i * stride + e] = dv; }
     }
   }
   if (done || resample) step = 0;
   if (k == 0) {
-    p.st.last_contact[e] = cbits;
-    p.st.step[e] = step;
-    p.st.kick[e] = kick0; p.st.kick[stride + e] = kick1;
+    if (valid) p.st.last_contact[e] = cbits;
+    if (valid) p.st.step[e] = step;
+    if (valid) p.st.kick[e] = kick0; if (valid) p.st.kick[stride + e] = kick1;
   }
 
   // ---- fused brax EpisodeWrapper + AutoResetWrapper ---------------------------------------------------
@@ -549,36 +555,36 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
 #pragma unroll
         for (int q = 0; q < PUPPER_NREWARD; q++) if (q + 1 == i) mv = rw[q];
         float v = (p.ep.sum_metrics[(size_t)i * es_ + e] + mv) * keep;
-        p.ep.sum_metrics[(size_t)i * es_ + e] = v;
+        if (valid) p.ep.sum_metrics[(size_t)i * es_ + e] = v;
         ep_metric[t] = v;
       }
     }
     __syncwarp(qm);
     if (k == 0) {
-      p.ep.steps[e] = steps; p.ep.truncation[e] = truncation; p.ep.sum_reward[e] = sum_reward; p.ep.length[e] = length;
-      p.ep.episode_done[e] = fdone;
+      if (valid) p.ep.steps[e] = steps; if (valid) p.ep.truncation[e] = truncation; if (valid) p.ep.sum_reward[e] = sum_reward; if (valid) p.ep.length[e] = length;
+      if (valid) p.ep.episode_done[e] = fdone;
     }
     if (p.ep.totals) {
       if (fdone != 0.f) {  // completed episode: add its sums to the device accumulator (all-reduced by the host side)
-        if (k == 0) { atomicAdd(p.ep.totals + 0, 1.f); atomicAdd(p.ep.totals + 1, sum_reward); atomicAdd(p.ep.totals + 2, length); atomicAdd(p.ep.totals + 22, done ? 1.f : 0.f); }
+        if (k == 0) { if (valid) atomicAdd(p.ep.totals + 0, 1.f); if (valid) atomicAdd(p.ep.totals + 1, sum_reward); if (valid) atomicAdd(p.ep.totals + 2, length); if (valid) atomicAdd(p.ep.totals + 22, done ? 1.f : 0.f); }
 #pragma unroll
-        for (int t = 0; t < 5; t++) if (k + 4 * t < PUPPER_NMETRIC) atomicAdd(p.ep.totals + 3 + k + 4 * t, ep_metric[t]);
+        for (int t = 0; t < 5; t++) if (k + 4 * t < PUPPER_NMETRIC) if (valid) atomicAdd(p.ep.totals + 3 + k + 4 * t, ep_metric[t]);
       }
     }
     if (fdone != 0.f) {  // AutoResetWrapper: restore the first pipeline state and first obs
-      for (int i = k; i < PUPPER_NQ; i += 4) p.st.qpos[(size_t)i * stride + e] = p.ep.first_qpos[(size_t)i * es_ + e];
+      for (int i = k; i < PUPPER_NQ; i += 4) if (valid) p.st.qpos[(size_t)i * stride + e] = p.ep.first_qpos[(size_t)i * es_ + e];
       for (int i = k; i < PUPPER_NV; i += 4) {
-        p.st.qvel[(size_t)i * stride + e] = p.ep.first_qvel[(size_t)i * es_ + e];
-        p.st.qacc_warmstart[(size_t)i * stride + e] = p.ep.first_warmstart[(size_t)i * es_ + e];
+        if (valid) p.st.qvel[(size_t)i * stride + e] = p.ep.first_qvel[(size_t)i * es_ + e];
+        if (valid) p.st.qacc_warmstart[(size_t)i * stride + e] = p.ep.first_warmstart[(size_t)i * es_ + e];
       }
-      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i];
+      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) if (valid) p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i];
     }
   }
 
   // ---- S12 outputs ------------------------------------------------------------------------------------------------------
-  if (k == 0) { p.out.reward[e] = reward; p.out.done[e] = fdone; p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
+  if (k == 0) { if (valid) p.out.reward[e] = reward; if (valid) p.out.done[e] = fdone; if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
 #pragma unroll
-  for (int q = 0; q < PUPPER_NREWARD; q++) if ((q & 3) == k) p.out.metrics[(size_t)e * PUPPER_NMETRIC + 1 + q] = rw[q];
+  for (int q = 0; q < PUPPER_NREWARD; q++) if ((q & 3) == k) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + 1 + q] = rw[q];
 }
 
 }  // namespace pupper
@@ -590,12 +596,24 @@ struct PupperModel {
   int device;
   PupperModelDesc *d_desc;
   PupperEnvCfg *d_cfg;
+  pupper::DerivedConsts *d_derived;
   PupperModelDesc h_desc;
   PupperEnvCfg h_cfg;
   int last_launches;
 };
 
 static thread_local char g_cuda_err[256] = "";
+
+// host twin of kbi() at pos = 0 (friction-loss rows)
+static void host_kbi(const float *solref, const float *solimp, float timestep, float &k, float &b, float &imp) {
+  float timeconst = fmaxf(solref[0], 2.f * timestep), dampratio = solref[1];
+  float dmin = fminf(fmaxf(solimp[0], 1e-4f), 0.9999f), dmax = fminf(fmaxf(solimp[1], 1e-4f), 0.9999f);
+  k = 1.f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  b = 2.f / (dmax * timeconst);
+  if (solref[0] <= 0.f) k = -solref[0] / (dmax * dmax);
+  if (solref[1] <= 0.f) b = -solref[1] / dmax;
+  imp = dmin;  // x = 0 < mid: imp = dmin + 0 * (dmax - dmin)
+}
 
 static int cuda_fail(cudaError_t e, const char *what) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
@@ -655,13 +673,36 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
   m->h_desc = *desc;
   m->h_cfg = *cfg;
   m->last_launches = 0;
+  // constants that do not depend on the state: friction-loss rows have pos = 0, so their impedance is fixed
+  pupper::DerivedConsts dc;
+  memset(&dc, 0, sizeof(dc));
+  {
+    float kk, bb, imp;
+    host_kbi(desc->dof_solref, desc->dof_solimp, desc->timestep, kk, bb, imp);
+    dc.fric_b = bb;
+    for (int d = 0; d < PUPPER_NV; d++) {
+      bool on = desc->frictionloss_rows && d >= 6 && desc->dof_frictionloss[d] > 0.f;
+      float R = fmaxf(desc->dof_invweight0[d] * (1.f - imp) / imp, 1e-15f);
+      dc.fric_loss[d] = on ? desc->dof_frictionloss[d] : 0.f;
+      dc.fric_D[d] = 1.f / R;
+      dc.fric_rf[d] = dc.fric_loss[d] / dc.fric_D[d];
+    }
+    for (int b = 0; b < desc->nbox; b++)
+      dc.box_rbound[b] = sqrtf(desc->box_size[b][0] * desc->box_size[b][0] + desc->box_size[b][1] * desc->box_size[b][1] + desc->box_size[b][2] * desc->box_size[b][2]);
+  }
+  m->d_desc = nullptr; m->d_cfg = nullptr; m->d_derived = nullptr;
   e = cudaMalloc(&m->d_desc, sizeof(PupperModelDesc));
-  if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc"); }
-  e = cudaMalloc(&m->d_cfg, sizeof(PupperEnvCfg));
-  if (e != cudaSuccess) { cudaFree(m->d_desc); delete m; return cuda_fail(e, "cudaMalloc"); }
-  e = cudaMemcpy(m->d_desc, desc, sizeof(PupperModelDesc), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_cfg, sizeof(PupperEnvCfg));
+  if (e == cudaSuccess) e = cudaMalloc(&m->d_derived, sizeof(pupper::DerivedConsts));
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_desc, desc, sizeof(PupperModelDesc), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_cfg, cfg, sizeof(PupperEnvCfg), cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) { cudaFree(m->d_desc); cudaFree(m->d_cfg); delete m; return cuda_fail(e, "cudaMemcpy"); }
+  if (e == cudaSuccess) e = cudaMemcpy(m->d_derived, &dc, sizeof(dc), cudaMemcpyHostToDevice);
+  const int smem = (int)sizeof(pupper::BlockShared);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { cudaFree(m->d_desc); cudaFree(m->d_cfg); cudaFree(m->d_derived); delete m; return cuda_fail(e, "pupper_model_create"); }
   *out = m;
   return PUPPER_OK;
 }
@@ -671,6 +712,7 @@ int pupper_model_destroy(PupperModel *m) {
   cudaSetDevice(m->device);
   cudaFree(m->d_desc);
   cudaFree(m->d_cfg);
+  cudaFree(m->d_derived);
   delete m;
   return PUPPER_OK;
 }
@@ -696,6 +738,7 @@ static pupper::KParams make_params(const PupperModel *model, int n_envs, const P
   memset(&p, 0, sizeof(p));
   p.model = model->d_desc;
   p.cfg = model->d_cfg;
+  p.derived = model->d_derived;
   p.n_envs = n_envs;
   p.st = *st;
   if (dr) { p.dr = *dr; p.has_dr = 1; }
@@ -719,8 +762,8 @@ int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, con
   pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, 0, s>>>(p);
-  else pupper::env_kernel<true, false><<<grid, pupper::kBlock, 0, s>>>(p);
+  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
+  else pupper::env_kernel<true, false><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_reset launch");
   const_cast<PupperModel *>(model)->last_launches = 1;
@@ -735,8 +778,8 @@ int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, Pupper
   pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, 0, s>>>(p);
-  else pupper::env_kernel<false, false><<<grid, pupper::kBlock, 0, s>>>(p);
+  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
+  else pupper::env_kernel<false, false><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_step launch");
   const_cast<PupperModel *>(model)->last_launches = 1;

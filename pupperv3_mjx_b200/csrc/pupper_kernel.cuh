@@ -29,9 +29,11 @@ constexpr int kMaxCon = 5 + 3;        // == PUPPER_MAX_CON
 constexpr float kMinVal = 1e-15f, kMinImp = 1e-4f, kMaxImp = 0.9999f;
 constexpr float kInf = 3.0e38f;
 
+struct DerivedConsts;
 struct KParams {
   const PupperModelDesc *model;  // device copies
   const PupperEnvCfg *cfg;
+  const DerivedConsts *derived;
   int n_envs;
   PupperState st;
   PupperDR dr;
@@ -59,10 +61,20 @@ struct EnvShared {
   int ncon;
 };
 
+struct DerivedConsts {  // computed once on the host in pupper_model_create
+  float fric_loss[PUPPER_NV];  // friction loss of instantiated friction rows (0: no row)
+  float fric_D[PUPPER_NV];     // efc_D of the friction-loss rows (pos = 0 -> constant)
+  float fric_rf[PUPPER_NV];    // R * frictionloss: half-width of the quadratic zone
+  float fric_b;                // velocity gain of aref
+  float box_rbound[PUPPER_MAX_BOX];
+};
+
 struct BlockShared {
   PupperModelDesc m;
   PupperEnvCfg c;
+  DerivedConsts d;
   EnvShared env[kEnvsPerBlock];
+  float rows[3 * kMaxCon * kBlock];  // contact-edge row scalars: [buffer][contact][thread]
 };
 
 __device__ __forceinline__ float qsum(float v, unsigned qm) {
@@ -312,41 +324,12 @@ struct DbgOut {  // only filled when DBG
   float qacc_b[6], qacc_l[3];
 };
 
-struct Row {  // one scalar constraint row handled by this lane
-  float D, aref, jaref, jv;
-};
-
 // Per-lane participation in contact c: bits 0-1 depth as body1 (-), bits 2-3 depth as body2 (+).
 __device__ __forceinline__ int participation(const ContactSlot &s, int k) {
   int p = 0;
   if (s.code1 >= 0 && (s.code1 >> 2) == k) p |= (s.code1 & 3);
   if (s.code2 >= 0 && (s.code2 >> 2) == k) p |= (s.code2 & 3) << 2;
   return p;
-}
-
-// jq[c] = Jc v (normal, t1, t2 components) for every active contact, replicated over the quad
-__device__ __forceinline__ void contact_jv(const EnvShared &es, int ncon, const int *part, const S6 cd[3], const V3 ba[3], const V3 bo[3],
-                                           const float vb[6], const float vl[3], float jq[][3], unsigned qm) {
-  S6 W0;
-  W0.a = vb[3] * ba[0] + vb[4] * ba[1] + vb[5] * ba[2];
-  W0.l = V3{vb[0], vb[1], vb[2]} + vb[3] * bo[0] + vb[4] * bo[1] + vb[5] * bo[2];
-  S6 W1 = fma6(vl[1], cd[1], fma6(vl[0], cd[0], W0));
-  S6 W2 = fma6(vl[2], cd[2], W1);
-#pragma unroll
-  for (int c = 0; c < kMaxCon; c++) {
-    if (c < ncon) {
-      const ContactSlot &s = es.con[c];
-      V3 r = V3{s.r[0], s.r[1], s.r[2]};
-      int d1 = part[c] & 3, d2 = (part[c] >> 2) & 3;
-      V3 pv = V3{0.f, 0.f, 0.f};
-      if (d2) { const S6 &W = d2 == 1 ? W1 : W2; pv = pv + (W.l + cross(W.a, r)); }
-      if (d1) { const S6 &W = d1 == 1 ? W1 : W2; pv = pv - (W.l + cross(W.a, r)); }
-      pv = qsum3(pv, qm);
-      jq[c][0] = s.frame[0] * pv.x + s.frame[1] * pv.y + s.frame[2] * pv.z;
-      jq[c][1] = s.frame[3] * pv.x + s.frame[4] * pv.y + s.frame[5] * pv.z;
-      jq[c][2] = s.frame[6] * pv.x + s.frame[7] * pv.y + s.frame[8] * pv.z;
-    }
-  }
 }
 
 // friction-loss row zone at residual x: 1 quadratic, 2 linear (x <= -R f), 3 linear (x >= R f)
@@ -359,11 +342,141 @@ __device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
   return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
 }
 
+// Row scalars of every active contact for this lane's pyramid edge: out[n][c] = (Jn + esgn*mu*Jt) . v_n
+// for N generalized vectors at once (v = [vb (6, replicated) | vl (this leg's 3)]).  Written to shared
+// memory at out[(n*kMaxCon + c)*kBlock].
+template <int N>
+__device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int k, const S6 cd[3], const V3 ba[3], const V3 bo[3],
+                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int ncon_w, float *out) {
+  S6 W1[N];  // spatial velocity of this leg's link2 (depth 1) under v_n; link3 adds vl[2]*cd[2]
+#pragma unroll
+  for (int n = 0; n < N; n++) {
+    S6 W0;
+    W0.a = vb[n][3] * ba[0] + vb[n][4] * ba[1] + vb[n][5] * ba[2];
+    W0.l = V3{vb[n][0], vb[n][1], vb[n][2]} + vb[n][3] * bo[0] + vb[n][4] * bo[1] + vb[n][5] * bo[2];
+    W1[n] = fma6(vl[n][1], cd[1], fma6(vl[n][0], cd[0], W0));
+  }
+#pragma unroll 1
+  for (int c = 0; c < ncon_w; c++) {  // ncon_w: warp-wide maximum, so the shuffles below stay convergent
+    const ContactSlot &s = es.con[c];
+    const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+    const int pc = c < ncon ? participation(s, k) : 0;
+    const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
+    const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
+    V3 pv[N];
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      S6 W = fma6(dep == 2 ? vl[n][2] : 0.f, cd[2], W1[n]);
+      V3 t = W.l + cross(W.a, r);
+      pv[n] = dep ? V3{sg * t.x, sg * t.y, sg * t.z} : V3{0.f, 0.f, 0.f};
+    }
+#pragma unroll
+    for (int n = 0; n < N; n++) pv[n] = qsum3(pv[n], qm);
+    const float t0 = et2 ? s.frame[6] : s.frame[3], t1 = et2 ? s.frame[7] : s.frame[4], t2 = et2 ? s.frame[8] : s.frame[5];
+    const float em = esgn * s.mu;
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+      float jn = s.frame[0] * pv[n].x + s.frame[1] * pv[n].y + s.frame[2] * pv[n].z;
+      float jt = t0 * pv[n].x + t1 * pv[n].y + t2 * pv[n].z;
+      out[(n * kMaxCon + c) * kBlock] = fmaf(em, jt, jn);
+    }
+  }
+}
+
+// Rare path: a leg-leg sphere contact couples two legs, so the Hessian is no longer arrow-shaped.
+// Gather the system on lane 0 of the quad and solve it densely (H holds M + diagonal row terms).
+__device__ __noinline__ void dense_newton_direction(const EnvShared &es, int ncon, int k, bool need, int qbase, const TreeMat &H,
+                                                    const float gb[6], const float gl[3], const S6 cd[3], const V3 ba[3], const V3 bo[3],
+                                                    const float *rowJ, float hb[6], float hl[3]) {
+  const unsigned qm = 0xffffffffu;
+  float Hd[18 * 18], Ld[18 * 18], xd[18], yd[18];
+  float cdall[12][6];
+  for (int i = 0; i < 18 * 18; i++) Hd[i] = 0.f;
+  for (int i = 0; i < 18; i++) xd[i] = 0.f;
+  for (int kk = 0; kk < 4; kk++) {
+    for (int j = 0; j < 3; j++) {
+      float c6[6] = {cd[j].a.x, cd[j].a.y, cd[j].a.z, cd[j].l.x, cd[j].l.y, cd[j].l.z};
+      for (int i = 0; i < 6; i++) cdall[3 * kk + j][i] = __shfl_sync(qm, c6[i], qbase + kk);
+      for (int d = 0; d < 6; d++) { float v = __shfl_sync(qm, H.C[j][d], qbase + kk); Hd[(6 + 3 * kk + j) * 18 + d] = v; Hd[d * 18 + 6 + 3 * kk + j] = v; }
+      for (int jj = 0; jj <= j; jj++) {
+        float v = __shfl_sync(qm, H.D[tri(j, jj)], qbase + kk);
+        Hd[(6 + 3 * kk + j) * 18 + 6 + 3 * kk + jj] = v; Hd[(6 + 3 * kk + jj) * 18 + 6 + 3 * kk + j] = v;
+      }
+      yd[6 + 3 * kk + j] = __shfl_sync(qm, gl[j], qbase + kk);
+    }
+  }
+  for (int i = 0; i < 6; i++) { yd[i] = gb[i]; for (int j = 0; j <= i; j++) { Hd[i * 18 + j] = H.B[tri(i, j)]; Hd[j * 18 + i] = H.B[tri(i, j)]; } }
+  float dall[kMaxCon][4];  // active-row weights of every contact's 4 pyramid edges
+  for (int c = 0; c < kMaxCon; c++) {
+    float de = 0.f;
+    if (c < ncon && rowJ[c * kBlock] < 0.f) de = es.con[c].D;
+    for (int e = 0; e < 4; e++) dall[c][e] = __shfl_sync(qm, de, qbase + e);
+  }
+  if (k == 0 && need) {
+    for (int c = 0; c < ncon; c++) {
+      const ContactSlot &s = es.con[c];
+      V3 r = V3{s.r[0], s.r[1], s.r[2]};
+      float Jc[3][18];
+      for (int d = 0; d < 18; d++) {
+        V3 col = V3{0.f, 0.f, 0.f};
+        for (int side = 0; side < 2; side++) {
+          int code = side ? s.code2 : s.code1;
+          if (code < 0) continue;
+          float sg = side ? 1.f : -1.f;
+          int leg = code >> 2, dep = code & 3;
+          V3 cc = V3{0.f, 0.f, 0.f};
+          if (d < 3) cc = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
+          else if (d < 6) cc = bo[d - 3] + cross(ba[d - 3], r);
+          else if ((d - 6) / 3 == leg && (d - 6) % 3 <= dep) {
+            const float *q = cdall[d - 6];
+            cc = V3{q[3], q[4], q[5]} + cross(V3{q[0], q[1], q[2]}, r);
+          }
+          col = col + sg * cc;
+        }
+        for (int i = 0; i < 3; i++) Jc[i][d] = s.frame[3 * i] * col.x + s.frame[3 * i + 1] * col.y + s.frame[3 * i + 2] * col.z;
+      }
+      for (int e = 0; e < 4; e++) {
+        float de = dall[c][e];
+        if (de == 0.f) continue;
+        float sg = (e & 1) ? -s.mu : s.mu;
+        const float *Jt = Jc[1 + (e >> 1)];
+        for (int i = 0; i < 18; i++) {
+          float ji = (Jc[0][i] + sg * Jt[i]) * de;
+          if (ji == 0.f) continue;
+          for (int j = 0; j < 18; j++) Hd[i * 18 + j] += ji * (Jc[0][j] + sg * Jt[j]);
+        }
+      }
+    }
+    for (int i = 0; i < 18; i++)
+      for (int j = 0; j <= i; j++) {
+        float s = Hd[i * 18 + j];
+        for (int p = 0; p < j; p++) s -= Ld[i * 18 + p] * Ld[j * 18 + p];
+        Ld[i * 18 + j] = (i == j) ? sqrtf(s) : s / Ld[j * 18 + j];
+      }
+    for (int i = 0; i < 18; i++) {
+      float s = yd[i];
+      for (int p = 0; p < i; p++) s -= Ld[i * 18 + p] * xd[p];
+      xd[i] = s / Ld[i * 18 + i];
+    }
+    for (int i = 17; i >= 0; i--) {
+      float s = xd[i];
+      for (int p = i + 1; p < 18; p++) s -= Ld[p * 18 + i] * xd[p];
+      xd[i] = s / Ld[i * 18 + i];
+    }
+  }
+  for (int d = 0; d < 6; d++) { float v = __shfl_sync(qm, xd[d], qbase); if (need) hb[d] = v; }
+  for (int kk = 0; kk < 4; kk++)
+    for (int j = 0; j < 3; j++) {
+      float v = __shfl_sync(qm, xd[6 + 3 * kk + j], qbase);
+      if (kk == k && need) hl[j] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One mjx.forward for the env of this quad.  Outputs qacc (ab, al).
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
-__device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, LaneState &L, int k, unsigned qm, int qbase,
+__device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, float *rows, LaneState &L, int k, unsigned qm, int qbase,
                                      float ab[6], float al[3], bool want_stale, StaleOut &so, DbgOut *dbg) {
   const PupperModelDesc &m = sh.m;
   const int b0 = 2 + 3 * k;   // first body of this leg
@@ -586,8 +699,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
           for (int bx = 0; bx < nbox; bx++) {
             if ((taken >> bx) & 1u) continue;
             V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sc[i];
-            float rb = sqrtf(m.box_size[bx][0] * m.box_size[bx][0] + m.box_size[bx][1] * m.box_size[bx][1] + m.box_size[bx][2] * m.box_size[bx][2]);
-            float key = sqrtf(dot(d, d)) - (m.sphere_radius[2 * k + i] + rb);
+            float key = sqrtf(dot(d, d)) - (m.sphere_radius[2 * k + i] + sh.d.box_rbound[bx]);
             int id = (2 * k + i) * nbox + bx;
             if (key < bk || (key == bk && id < bi)) { bk = key; bi = id; }
           }
@@ -628,8 +740,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
         pa[i] = a; pb[i] = b;
         any_neg |= pd[i] < 0.f;
       }
-      unsigned anyq = __ballot_sync(qm, any_neg) & qm;
-      if (anyq) {
+      if (__any_sync(qm, any_neg)) {  // warp-uniform
         uint32_t taken = 0u;
         for (int r = 0; r < maxp && r < 24; r++) {
           float bk = kInf;
@@ -682,8 +793,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
         int oi = __shfl_xor_sync(qm, mi, s);
         if (ok < mk || (ok == mk && oi < mi)) { mk = ok; mi = oi; }
       }
-      if (!(mk < 0.f)) break;  // uniform over the quad
-      if (mi == bi && bk < 0.f) {  // this lane owns the winner: publish slot r
+      if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
+      if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish slot r
         ContactSlot &s = es.con[r];
         V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
         int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
@@ -711,129 +822,118 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
         s.mu = mu; s.D = 1.f / Rr; s.b = bb; s.kimp = kk * imp * bk; s.dist = bk;
         s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2;
       }
-      ncon = r + 1;
+      if (mk < 0.f) ncon = r + 1;
     }
   }
   __syncwarp(qm);  // contact slots visible to the quad
-  int part[kMaxCon];
+  const int ncon_w = __reduce_max_sync(qm, ncon);
   bool any_ss = false;
   float knee_hits = 0.f, torso_hits = 0.f;
-#pragma unroll
-  for (int c = 0; c < kMaxCon; c++) {
-    part[c] = 0;
-    if (c < ncon) {
-      const ContactSlot &s = es.con[c];
-      part[c] = participation(s, k);
-      any_ss |= (s.code1 >= 0 && s.code2 >= 0);
-      if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
-      if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
-    }
+#pragma unroll 1
+  for (int c = 0; c < ncon; c++) {
+    const ContactSlot &s = es.con[c];
+    any_ss |= (s.code1 >= 0 && s.code2 >= 0);
+    if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
+    if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
 
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
-  const bool has_f = m.frictionloss_rows != 0;
-  Row rf[3], rl[3], rc[kMaxCon];
-  float fl[3], rff[3];   // friction loss and R*f per friction row
-  float lsign[3];        // limit row Jacobian entry (+-1, 0 when inactive)
-  float jq[kMaxCon][3];
-  contact_jv(es, ncon, part, cd, ba, bo, L.vb, L.vl, jq, qm);
+  // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
+  float *rowA = rows + threadIdx.x, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
   const float esgn = (k & 1) ? -1.f : 1.f;  // pyramid edge of this lane: Jn + esgn*mu*Jt[k>>1]
-  const int et = 1 + (k >> 1);
+  const bool et2 = (k >> 1) != 0;
+  float fl[3], rff[3], fD[3], fA[3];   // friction-loss rows: loss, R*loss, D, aref
+  float lD[3], lA[3], lsign[3];        // limit rows: D, aref, Jacobian entry (+-1, 0 when inactive)
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const int d = 6 + 3 * k + j;
-    float kk, bb, imp;
-    fl[j] = (has_f && m.dof_frictionloss[d] > 0.f) ? m.dof_frictionloss[d] : 0.f;
-    kbi(m.dof_solref, m.dof_solimp, dt, 0.f, kk, bb, imp);
-    float Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
-    rf[j].D = 1.f / Rr;
-    rf[j].aref = -bb * L.vl[j];
-    rff[j] = fl[j] / rf[j].D;
+    fl[j] = sh.d.fric_loss[d];
+    fD[j] = sh.d.fric_D[d];
+    rff[j] = sh.d.fric_rf[d];
+    fA[j] = -sh.d.fric_b * L.vl[j];
     float dlo = L.ql[j] - m.jnt_range[3 * k + j][0], dhi = m.jnt_range[3 * k + j][1] - L.ql[j];
     float p = fminf(dlo, dhi);
-    bool act = p < 0.f;
-    lsign[j] = act ? (dlo < dhi ? 1.f : -1.f) : 0.f;
-    kbi(m.jnt_solref, m.jnt_solimp, dt, act ? p : 0.f, kk, bb, imp);
-    Rr = fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
-    rl[j].D = 1.f / Rr;
-    rl[j].aref = -bb * (lsign[j] * L.vl[j]) - kk * imp * (act ? p : 0.f);
-  }
-#pragma unroll
-  for (int c = 0; c < kMaxCon; c++) {
-    if (c < ncon) {
-      const ContactSlot &s = es.con[c];
-      rc[c].D = s.D;
-      rc[c].aref = -s.b * (jq[c][0] + esgn * s.mu * jq[c][et]) - s.kimp;
+    lsign[j] = 0.f; lD[j] = 0.f; lA[j] = 0.f;
+    if (p < 0.f) {
+      float kk, bb, imp;
+      lsign[j] = dlo < dhi ? 1.f : -1.f;
+      kbi(m.jnt_solref, m.jnt_solimp, dt, p, kk, bb, imp);
+      lD[j] = 1.f / fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
+      lA[j] = -bb * (lsign[j] * L.vl[j]) - kk * imp * p;
     }
   }
 
   // ---- unconstrained acceleration: M qacc_smooth = qfrc_smooth ---------------------------------------------
-  TreeMat F = M;
-  tree_factor(F, nullptr, qm);
   float sb[6], sl[3];
-  tree_solve(F, fs_b, fs_l, sb, sl, qm);
+  {
+    TreeMat F = M;
+    tree_factor(F, nullptr, qm);
+    tree_solve(F, fs_b, fs_l, sb, sl, qm);
+  }
 
   // ---- Newton solver, one iteration (A.8) ------------------------------------------------------------------
-  // cost at the warm start and at qacc_smooth
-  float cost_w, cost_s, gauss_w;
-  float Maw_b[6], Maw_l[3], Mas_b[6], Mas_l[3];
-  float jaw_f[3], jaw_l[3], jaw_c[kMaxCon], jas_f[3], jas_l[3], jas_c[kMaxCon];
+  // cost at the warm start and at qacc_smooth.  (M qacc_smooth is taken as qfrc_smooth.)
+  float Maw_b[6], Maw_l[3];
+  tree_matvec(M, L.wb, L.wl, Maw_b, Maw_l, qm);
   {
-    tree_matvec(M, L.wb, L.wl, Maw_b, Maw_l, qm);
-    tree_matvec(M, sb, sl, Mas_b, Mas_l, qm);
-    float jqw[kMaxCon][3], jqs[kMaxCon][3];
-    contact_jv(es, ncon, part, cd, ba, bo, L.wb, L.wl, jqw, qm);
-    contact_jv(es, ncon, part, cd, ba, bo, sb, sl, jqs, qm);
+    float v3b[3][6], v3l[3][3];
+#pragma unroll
+    for (int d = 0; d < 6; d++) { v3b[0][d] = L.vb[d]; v3b[1][d] = L.wb[d]; v3b[2][d] = sb[d]; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { v3l[0][j] = L.vl[j]; v3l[1][j] = L.wl[j]; v3l[2][j] = sl[j]; }
+    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, ncon_w, rowA);
+  }
+  float cost_w, cost_s, gauss_w;
+  float jaw_f[3], jaw_l[3], jas_f[3], jas_l[3];
+  {
     float cw = 0.f, cs = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
+      jaw_f[j] = 0.f; jas_f[j] = 0.f;
       if (fl[j] > 0.f) {
-        float xw = L.wl[j] - rf[j].aref, xs = sl[j] - rf[j].aref;
+        float xw = L.wl[j] - fA[j], xs = sl[j] - fA[j];
         jaw_f[j] = xw; jas_f[j] = xs;
         int zw = fzone(xw, rff[j]), zs = fzone(xs, rff[j]);
-        cw += zw == 1 ? 0.5f * rf[j].D * xw * xw : (zw == 2 ? fl[j] * (-0.5f * rff[j] - xw) : fl[j] * (-0.5f * rff[j] + xw));
-        cs += zs == 1 ? 0.5f * rf[j].D * xs * xs : (zs == 2 ? fl[j] * (-0.5f * rff[j] - xs) : fl[j] * (-0.5f * rff[j] + xs));
-      } else { jaw_f[j] = 0.f; jas_f[j] = 0.f; }
-      float xw = lsign[j] * L.wl[j] - rl[j].aref, xs = lsign[j] * sl[j] - rl[j].aref;
-      jaw_l[j] = xw; jas_l[j] = xs;
-      if (xw < 0.f) cw += 0.5f * rl[j].D * xw * xw;
-      if (xs < 0.f) cs += 0.5f * rl[j].D * xs * xs;
-    }
-#pragma unroll
-    for (int c = 0; c < kMaxCon; c++) {
-      if (c < ncon) {
-        float mu = es.con[c].mu;
-        float xw = jqw[c][0] + esgn * mu * jqw[c][et] - rc[c].aref, xs = jqs[c][0] + esgn * mu * jqs[c][et] - rc[c].aref;
-        jaw_c[c] = xw; jas_c[c] = xs;
-        if (xw < 0.f) cw += 0.5f * rc[c].D * xw * xw;
-        if (xs < 0.f) cs += 0.5f * rc[c].D * xs * xs;
+        cw += zw == 1 ? 0.5f * fD[j] * xw * xw : (zw == 2 ? fl[j] * (-0.5f * rff[j] - xw) : fl[j] * (-0.5f * rff[j] + xw));
+        cs += zs == 1 ? 0.5f * fD[j] * xs * xs : (zs == 2 ? fl[j] * (-0.5f * rff[j] - xs) : fl[j] * (-0.5f * rff[j] + xs));
       }
+      float xw = lsign[j] * L.wl[j] - lA[j], xs = lsign[j] * sl[j] - lA[j];
+      jaw_l[j] = xw; jas_l[j] = xs;
+      if (xw < 0.f) cw += 0.5f * lD[j] * xw * xw;
+      if (xs < 0.f) cs += 0.5f * lD[j] * xs * xs;
     }
-    // Gauss terms: leg part summed over the quad, base part replicated
-    float gw = 0.f, gs = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {
+      const ContactSlot &s = es.con[c];
+      float aref = -s.b * rowA[c * kBlock] - s.kimp;
+      float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
+      rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;   // now Jaref at the warm start / at qacc_smooth
+      if (xw < 0.f) cw += 0.5f * s.D * xw * xw;
+      if (xs < 0.f) cs += 0.5f * s.D * xs * xs;
+    }
+    float gw = 0.f;
 #pragma unroll
-    for (int j = 0; j < 3; j++) { gw = fmaf(Maw_l[j] - fs_l[j], L.wl[j] - sl[j], gw); }
+    for (int j = 0; j < 3; j++) gw = fmaf(Maw_l[j] - fs_l[j], L.wl[j] - sl[j], gw);
     gw = qsum(gw, qm);
 #pragma unroll
     for (int d = 0; d < 6; d++) gw = fmaf(Maw_b[d] - fs_b[d], L.wb[d] - sb[d], gw);
-    (void)gs;
     gauss_w = 0.5f * gw;
     cost_w = qsum(cw, qm) + gauss_w;
     cost_s = qsum(cs, qm);  // gauss(qacc_smooth) = 0
   }
   const bool use_w = cost_w < cost_s;
+  float *rowJ = use_w ? rowB : rowC;  // Jaref of the contact-edge rows at the chosen start
   float xb[6], xl[3], Mab[6], Mal[3];  // qacc, M qacc
-  float gauss = use_w ? gauss_w : 0.f;
+  float fJ[3], lJ[3];
+  const float gauss = use_w ? gauss_w : 0.f;
 #pragma unroll
-  for (int d = 0; d < 6; d++) { xb[d] = use_w ? L.wb[d] : sb[d]; Mab[d] = use_w ? Maw_b[d] : Mas_b[d]; }
+  for (int d = 0; d < 6; d++) { xb[d] = use_w ? L.wb[d] : sb[d]; Mab[d] = use_w ? Maw_b[d] : fs_b[d]; }
 #pragma unroll
   for (int j = 0; j < 3; j++) {
-    xl[j] = use_w ? L.wl[j] : sl[j]; Mal[j] = use_w ? Maw_l[j] : Mas_l[j];
-    rf[j].jaref = use_w ? jaw_f[j] : jas_f[j];
-    rl[j].jaref = use_w ? jaw_l[j] : jas_l[j];
+    xl[j] = use_w ? L.wl[j] : sl[j]; Mal[j] = use_w ? Maw_l[j] : fs_l[j];
+    fJ[j] = use_w ? jaw_f[j] : jas_f[j];
+    lJ[j] = use_w ? jaw_l[j] : jas_l[j];
   }
-#pragma unroll
-  for (int c = 0; c < kMaxCon; c++) if (c < ncon) rc[c].jaref = use_w ? jaw_c[c] : jas_c[c];
 
   // forces, J^T f, gradient; Hessian additions
   float gb[6], gl[3];
@@ -846,70 +946,68 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       if (fl[j] > 0.f) {
-        int z = fzone(rf[j].jaref, rff[j]);
-        qc_l[j] += z == 1 ? -rf[j].D * rf[j].jaref : (z == 2 ? fl[j] : -fl[j]);
-        if (z == 1) H.D[tri(j, j)] += rf[j].D;
+        int z = fzone(fJ[j], rff[j]);
+        qc_l[j] += z == 1 ? -fD[j] * fJ[j] : (z == 2 ? fl[j] : -fl[j]);
+        if (z == 1) H.D[tri(j, j)] += fD[j];
       }
-      if (rl[j].jaref < 0.f) {
-        qc_l[j] += lsign[j] * (-rl[j].D * rl[j].jaref);
-        H.D[tri(j, j)] += rl[j].D * lsign[j] * lsign[j];
+      if (lJ[j] < 0.f) {
+        qc_l[j] += lsign[j] * (-lD[j] * lJ[j]);
+        H.D[tri(j, j)] += lD[j];
       }
     }
     S6 S1 = S6{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, S2 = S1, Sb = S1;  // wrenches on link2 / link3 chains, base
+#pragma unroll 1
+    for (int c = 0; c < ncon_w; c++) {
+      const ContactSlot &s = es.con[c];
+      const bool con_on = c < ncon;
+      const float ja = con_on ? rowJ[c * kBlock] : 0.f;
+      float act = ja < 0.f ? 1.f : 0.f;
+      float fe = -s.D * ja * act;  // force of this lane's pyramid edge
+      float de = s.D * act;
+      float f0 = __shfl_sync(qm, fe, qbase + 0), f1 = __shfl_sync(qm, fe, qbase + 1), f2 = __shfl_sync(qm, fe, qbase + 2), f3 = __shfl_sync(qm, fe, qbase + 3);
+      float d0 = __shfl_sync(qm, de, qbase + 0), d1 = __shfl_sync(qm, de, qbase + 1), d2 = __shfl_sync(qm, de, qbase + 2), d3 = __shfl_sync(qm, de, qbase + 3);
+      // contact-frame force and world wrench about C
+      float Fn = (f0 + f1) + (f2 + f3), Ft1 = s.mu * (f0 - f1), Ft2 = s.mu * (f2 - f3);
+      V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
+                s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
+      V3 r = V3{s.r[0], s.r[1], s.r[2]};
+      S6 w = S6{cross(r, g), g};
+      const int pc = con_on ? participation(s, k) : 0;
+      int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
+      float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
+      S1 = fma6(s1w, w, S1);
+      S2 = fma6(s2w, w, S2);
+      float wb_ = con_on ? (s.code2 >= 0 ? 1.f : 0.f) - (s.code1 >= 0 ? 1.f : 0.f) : 0.f;
+      Sb = fma6(wb_, w, Sb);
+      // Hessian: Jc^T W Jc with W from the 4 edge weights (world-vs-leg contacts only; see the dense path)
+      float sd = (d0 + d1) + (d2 + d3);
+      int dep = dd2 | dd1;
+      if (sd > 0.f && !any_ss && dep) {
+        float W00 = sd, W01 = s.mu * (d0 - d1), W02 = s.mu * (d2 - d3), W11 = s.mu * s.mu * (d0 + d1), W22 = s.mu * s.mu * (d2 + d3);
+        float Jc[9][3], T[9][3];
 #pragma unroll
-    for (int c = 0; c < kMaxCon; c++) {
-      if (c < ncon) {
-        const ContactSlot &s = es.con[c];
-        float act = rc[c].jaref < 0.f ? 1.f : 0.f;
-        float fe = -rc[c].D * rc[c].jaref * act;  // force of this lane's pyramid edge
-        float de = rc[c].D * act;
-        float f0 = __shfl_sync(qm, fe, qbase + 0), f1 = __shfl_sync(qm, fe, qbase + 1), f2 = __shfl_sync(qm, fe, qbase + 2), f3 = __shfl_sync(qm, fe, qbase + 3);
-        float d0 = __shfl_sync(qm, de, qbase + 0), d1 = __shfl_sync(qm, de, qbase + 1), d2 = __shfl_sync(qm, de, qbase + 2), d3 = __shfl_sync(qm, de, qbase + 3);
-        // contact-frame force and world wrench about C
-        float Fn = (f0 + f1) + (f2 + f3), Ft1 = s.mu * (f0 - f1), Ft2 = s.mu * (f2 - f3);
-        V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
-                  s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
-        V3 r = V3{s.r[0], s.r[1], s.r[2]};
-        S6 w = S6{cross(r, g), g};
-        int dd1 = part[c] & 3, dd2 = (part[c] >> 2) & 3;
-        float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
-        S1 = fma6(s1w, w, S1);
-        S2 = fma6(s2w, w, S2);
-        float wb_ = (s.code2 >= 0 ? 1.f : 0.f) - (s.code1 >= 0 ? 1.f : 0.f);
-        Sb = fma6(wb_, w, Sb);
-        // Hessian: Jc^T W Jc with W from the 4 edge weights
-        float sd = (d0 + d1) + (d2 + d3);
-        if (sd > 0.f && !any_ss) {
-          int dep = dd2 ? dd2 : dd1;       // world-vs-leg contact: exactly one side is this leg (or none)
-          if (dep) {
-            float W00 = sd, W01 = s.mu * (d0 - d1), W02 = s.mu * (d2 - d3), W11 = s.mu * s.mu * (d0 + d1), W22 = s.mu * s.mu * (d2 + d3);
-            // columns of Jc for the 6 base dofs and the leg dofs (sign cancels in J^T W J)
-            float Jc[9][3], T[9][3];
+        for (int d = 0; d < 9; d++) {
+          V3 col;
+          if (d < 3) col = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
+          else if (d < 6) col = bo[d - 3] + cross(ba[d - 3], r);
+          else col = (d - 6 <= dep) ? cd[d - 6].l + cross(cd[d - 6].a, r) : V3{0.f, 0.f, 0.f};
+          Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
+          Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
+          Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
+          T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
+          T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
+          T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
+        }
 #pragma unroll
-            for (int d = 0; d < 9; d++) {
-              V3 col;
-              if (d < 3) col = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
-              else if (d < 6) col = bo[d - 3] + cross(ba[d - 3], r);
-              else col = (d - 6 <= dep) ? cd[d - 6].l + cross(cd[d - 6].a, r) : V3{0.f, 0.f, 0.f};
-              Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
-              Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
-              Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
-              T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
-              T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
-              T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
-            }
+        for (int i = 0; i < 6; i++)
 #pragma unroll
-            for (int i = 0; i < 6; i++)
+          for (int j = 0; j <= i; j++) Badd[tri(i, j)] += T[i][0] * Jc[j][0] + T[i][1] * Jc[j][1] + T[i][2] * Jc[j][2];
 #pragma unroll
-              for (int j = 0; j <= i; j++) Badd[tri(i, j)] += T[i][0] * Jc[j][0] + T[i][1] * Jc[j][1] + T[i][2] * Jc[j][2];
+        for (int j = 0; j < 3; j++) {
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
+          for (int d = 0; d < 6; d++) H.C[j][d] += T[6 + j][0] * Jc[d][0] + T[6 + j][1] * Jc[d][1] + T[6 + j][2] * Jc[d][2];
 #pragma unroll
-              for (int d = 0; d < 6; d++) H.C[j][d] += T[6 + j][0] * Jc[d][0] + T[6 + j][1] * Jc[d][1] + T[6 + j][2] * Jc[d][2];
-#pragma unroll
-              for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
-            }
-          }
+          for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
         }
       }
     }
@@ -924,89 +1022,19 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
 
   // Newton direction: search = -H^-1 grad
   float hb[6], hl[3];
-  if (!any_ss) {
-    tree_factor(H, Badd, qm);
-    tree_solve(H, gb, gl, hb, hl, qm);
-  } else {
-    // ---- rare path: a leg-leg sphere contact couples two legs; gather to lane 0 and solve densely ----
-    float Hd[18 * 18], Ld[18 * 18], xd[18], yd[18];
-    float cdall[12][6];
-    for (int i = 0; i < 18 * 18; i++) Hd[i] = 0.f;
-    for (int kk = 0; kk < 4; kk++) {
-      for (int j = 0; j < 3; j++) {
-        float c6[6] = {cd[j].a.x, cd[j].a.y, cd[j].a.z, cd[j].l.x, cd[j].l.y, cd[j].l.z};
-        for (int i = 0; i < 6; i++) { float v = __shfl_sync(qm, c6[i], qbase + kk); cdall[3 * kk + j][i] = v; }
-        for (int d = 0; d < 6; d++) { float v = __shfl_sync(qm, H.C[j][d], qbase + kk); Hd[(6 + 3 * kk + j) * 18 + d] = v; Hd[d * 18 + 6 + 3 * kk + j] = v; }
-        for (int jj = 0; jj <= j; jj++) { float v = __shfl_sync(qm, H.D[tri(j, jj)], qbase + kk); Hd[(6 + 3 * kk + j) * 18 + 6 + 3 * kk + jj] = v; Hd[(6 + 3 * kk + jj) * 18 + 6 + 3 * kk + j] = v; }
-        float g = __shfl_sync(qm, gl[j], qbase + kk);
-        yd[6 + 3 * kk + j] = g;
-      }
+  if (__any_sync(qm, any_ss)) {  // rare: some env of this warp has a leg-leg contact (H still holds M + diagonal terms there)
+    dense_newton_direction(es, ncon, k, any_ss, qbase, H, gb, gl, cd, ba, bo, rowJ, hb, hl);
+  }
+  tree_factor(H, Badd, qm);
+  {
+    float tb[6], tl[3];
+    tree_solve(H, gb, gl, tb, tl, qm);
+    if (!any_ss) {
+#pragma unroll
+      for (int d = 0; d < 6; d++) hb[d] = tb[d];
+#pragma unroll
+      for (int j = 0; j < 3; j++) hl[j] = tl[j];
     }
-    for (int i = 0; i < 6; i++) { yd[i] = gb[i]; for (int j = 0; j <= i; j++) { Hd[i * 18 + j] = H.B[tri(i, j)]; Hd[j * 18 + i] = H.B[tri(i, j)]; } }
-    // edge weights of every contact (needed by lane 0)
-    float dall[kMaxCon][4];
-    for (int c = 0; c < kMaxCon; c++) {
-      float de = (c < ncon && rc[c].jaref < 0.f) ? rc[c].D : 0.f;
-      for (int e = 0; e < 4; e++) dall[c][e] = __shfl_sync(qm, de, qbase + e);
-    }
-    if (k == 0) {
-      for (int c = 0; c < ncon; c++) {
-        const ContactSlot &s = es.con[c];
-        V3 r = V3{s.r[0], s.r[1], s.r[2]};
-        float Jc[3][18];
-        for (int d = 0; d < 18; d++) {
-          V3 col = V3{0.f, 0.f, 0.f};
-          for (int side = 0; side < 2; side++) {
-            int code = side ? s.code2 : s.code1;
-            if (code < 0) continue;
-            float sg = side ? 1.f : -1.f;
-            int leg = code >> 2, dep = code & 3;
-            V3 cc = V3{0.f, 0.f, 0.f};
-            if (d < 3) cc = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
-            else if (d < 6) cc = bo[d - 3] + cross(ba[d - 3], r);
-            else if ((d - 6) / 3 == leg && (d - 6) % 3 <= dep) {
-              const float *q = cdall[d - 6];
-              cc = V3{q[3], q[4], q[5]} + cross(V3{q[0], q[1], q[2]}, r);
-            }
-            col = col + sg * cc;
-          }
-          for (int i = 0; i < 3; i++) Jc[i][d] = s.frame[3 * i] * col.x + s.frame[3 * i + 1] * col.y + s.frame[3 * i + 2] * col.z;
-        }
-        for (int e = 0; e < 4; e++) {
-          float de = dall[c][e];
-          if (de == 0.f) continue;
-          float sg = (e & 1) ? -s.mu : s.mu;
-          const float *Jt = Jc[1 + (e >> 1)];
-          for (int i = 0; i < 18; i++) {
-            float ji = (Jc[0][i] + sg * Jt[i]) * de;
-            if (ji == 0.f) continue;
-            for (int j = 0; j < 18; j++) Hd[i * 18 + j] += ji * (Jc[0][j] + sg * Jt[j]);
-          }
-        }
-      }
-      for (int i = 0; i < 18; i++)
-        for (int j = 0; j <= i; j++) {
-          float s = Hd[i * 18 + j];
-          for (int p = 0; p < j; p++) s -= Ld[i * 18 + p] * Ld[j * 18 + p];
-          Ld[i * 18 + j] = (i == j) ? sqrtf(s) : s / Ld[j * 18 + j];
-        }
-      for (int i = 0; i < 18; i++) {
-        float s = yd[i];
-        for (int p = 0; p < i; p++) s -= Ld[i * 18 + p] * xd[p];
-        xd[i] = s / Ld[i * 18 + i];
-      }
-      for (int i = 17; i >= 0; i--) {
-        float s = xd[i];
-        for (int p = i + 1; p < 18; p++) s -= Ld[p * 18 + i] * xd[p];
-        xd[i] = s / Ld[i * 18 + i];
-      }
-    }
-    for (int d = 0; d < 6; d++) hb[d] = __shfl_sync(qm, xd[d], qbase);
-    for (int kk = 0; kk < 4; kk++)
-      for (int j = 0; j < 3; j++) {
-        float v = __shfl_sync(qm, xd[6 + 3 * kk + j], qbase);
-        if (kk == k) hl[j] = v;
-      }
   }
 #pragma unroll
   for (int d = 0; d < 6; d++) hb[d] = -hb[d];
@@ -1018,73 +1046,102 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, La
   {
     float mvb[6], mvl[3];
     tree_matvec(M, hb, hl, mvb, mvl, qm);
-    float jqh[kMaxCon][3];
-    contact_jv(es, ncon, part, cd, ba, bo, hb, hl, jqh, qm);
+    {
+      float v1b[1][6], v1l[1][3];
+#pragma unroll
+      for (int d = 0; d < 6; d++) v1b[0][d] = hb[d];
+#pragma unroll
+      for (int j = 0; j < 3; j++) v1l[0][j] = hl[j];
+      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, ncon_w, rowA);  // jv of the contact-edge rows
+    }
     float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];
     float q1l = 0.f, q2l = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       q1l = fmaf(hl[j], Mal[j] - fs_l[j], q1l);
       q2l = fmaf(hl[j], mvl[j], q2l);
-      rf[j].jv = hl[j];
-      rl[j].jv = lsign[j] * hl[j];
     }
     sn = qsum(sn, qm); q1l = qsum(q1l, qm); q2l = qsum(q2l, qm);
 #pragma unroll
     for (int d = 0; d < 6; d++) { sn = fmaf(hb[d], hb[d], sn); q1l = fmaf(hb[d], Mab[d] - fs_b[d], q1l); q2l = fmaf(hb[d], mvb[d], q2l); }
     const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
     const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
-#pragma unroll
-    for (int c = 0; c < kMaxCon; c++) if (c < ncon) rc[c].jv = jqh[c][0] + esgn * es.con[c].mu * jqh[c][et];
 
-    // per-row quadratic coefficients (0.5 D Jaref^2, D jv Jaref, 0.5 D jv^2)
-    auto eval = [&](float a) -> LSPoint {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
+    auto eval3 = [&](const float a[3], LSPoint out[3]) {
+      float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         if (fl[j] > 0.f) {
-          float ja = rf[j].jaref, jv = rf[j].jv, x = fmaf(a, jv, ja);
-          int z = fzone(x, rff[j]);
-          if (z == 1) { s0 += 0.5f * ja * ja * rf[j].D; s1 += jv * ja * rf[j].D; s2 += 0.5f * jv * jv * rf[j].D; }
-          else if (z == 2) { s0 += fl[j] * (-0.5f * rff[j] - ja); s1 += -fl[j] * jv; }
-          else { s0 += fl[j] * (-0.5f * rff[j] + ja); s1 += fl[j] * jv; }
+          const float ja = fJ[j], jv = hl[j];
+          const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
+          const float ln = fl[j] * (-0.5f * rff[j] - ja), lp = fl[j] * (-0.5f * rff[j] + ja), lv = fl[j] * jv;
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            int z = fzone(fmaf(a[p], jv, ja), rff[j]);
+            s0[p] += z == 1 ? qa : (z == 2 ? ln : lp);
+            s1[p] += z == 1 ? qb : (z == 2 ? -lv : lv);
+            s2[p] += z == 1 ? qc : 0.f;
+          }
         }
-        {
-          float ja = rl[j].jaref, jv = rl[j].jv, x = fmaf(a, jv, ja);
-          if (x < 0.f) { s0 += 0.5f * ja * ja * rl[j].D; s1 += jv * ja * rl[j].D; s2 += 0.5f * jv * jv * rl[j].D; }
+        if (lsign[j] != 0.f) {
+          const float ja = lJ[j], jv = lsign[j] * hl[j];
+          const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            bool on = fmaf(a[p], jv, ja) < 0.f;
+            s0[p] += on ? qa : 0.f; s1[p] += on ? qb : 0.f; s2[p] += on ? qc : 0.f;
+          }
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncon; c++) {  // no shuffles inside: per-quad trip count is fine
+        const float ja = rowJ[c * kBlock], jv = rowA[c * kBlock], D = es.con[c].D;
+        const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+          bool on = fmaf(a[p], jv, ja) < 0.f;
+          s0[p] += on ? qa : 0.f; s1[p] += on ? qb : 0.f; s2[p] += on ? qc : 0.f;
         }
       }
 #pragma unroll
-      for (int c = 0; c < kMaxCon; c++) {
-        if (c < ncon) {
-          float ja = rc[c].jaref, jv = rc[c].jv, x = fmaf(a, jv, ja);
-          if (x < 0.f) { s0 += 0.5f * ja * ja * rc[c].D; s1 += jv * ja * rc[c].D; s2 += 0.5f * jv * jv * rc[c].D; }
-        }
+      for (int p = 0; p < 3; p++) {
+        float t0 = gq0 + qsum(s0[p], qm), t1 = gq1 + qsum(s1[p], qm), t2 = gq2 + qsum(s2[p], qm);
+        out[p].alpha = a[p];
+        out[p].cost = a[p] * a[p] * t2 + a[p] * t1 + t0;
+        out[p].d0 = 2.f * a[p] * t2 + t1;
+        out[p].d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
       }
-      float t0 = gq0 + qsum(s0, qm), t1 = gq1 + qsum(s1, qm), t2 = gq2 + qsum(s2, qm);
-      LSPoint p;
-      p.alpha = a;
-      p.cost = a * a * t2 + a * t1 + t0;
-      p.d0 = 2.f * a * t2 + t1;
-      p.d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
-      return p;
     };
-    LSPoint p0 = eval(0.f);
-    LSPoint lo = eval(p0.alpha - p0.d0 / p0.d1), hi;
-    if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
-    bool swap = true;
-    for (int it = 0; it < m.ls_iterations; it++) {
-      if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) break;
-      LSPoint lon = eval(lo.alpha - lo.d0 / lo.d1);
-      LSPoint hin = eval(hi.alpha - hi.d0 / hi.d1);
-      LSPoint mid = eval(0.5f * (lo.alpha + hi.alpha));
-      bool s1 = in_bracket(lo, lon); if (s1) lo = lon;
-      bool s2 = in_bracket(lo, mid); if (s2) lo = mid;
-      bool s3 = in_bracket(lo, hin); if (s3) lo = hin;
-      bool t1 = in_bracket(hi, hin); if (t1) hi = hin;
-      bool t2 = in_bracket(hi, mid); if (t2) hi = mid;
-      bool t3 = in_bracket(hi, lon); if (t3) hi = lon;
-      swap = s1 | s2 | s3 | t1 | t2 | t3;
+    LSPoint p0 = LSPoint{0.f, 0.f, 0.f, 1.f}, lo = p0, hi = p0;
+    bool swap = true, ls_on = true;
+    const int nstage = 2 + m.ls_iterations;
+#pragma unroll 1
+    for (int stage = 0; stage < nstage; stage++) {
+      float a3[3];
+      if (stage == 0) { a3[0] = a3[1] = a3[2] = 0.f; }
+      else if (stage == 1) { a3[0] = a3[1] = a3[2] = p0.alpha - p0.d0 / p0.d1; }
+      else {
+        if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) ls_on = false;
+        if (!__any_sync(qm, ls_on)) break;  // warp-uniform exit; finished envs idle through the remaining stages
+        a3[0] = lo.alpha - lo.d0 / lo.d1; a3[1] = hi.alpha - hi.d0 / hi.d1; a3[2] = 0.5f * (lo.alpha + hi.alpha);
+      }
+      LSPoint pt[3];
+      eval3(a3, pt);
+      if (stage == 0) { p0 = pt[0]; }
+      else if (stage == 1) {
+        lo = pt[0];
+        if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+      } else if (ls_on) {
+        const LSPoint lon = pt[0], hin = pt[1], mid = pt[2];
+        bool s1 = in_bracket(lo, lon); if (s1) lo = lon;
+        bool s2 = in_bracket(lo, mid); if (s2) lo = mid;
+        bool s3 = in_bracket(lo, hin); if (s3) lo = hin;
+        bool t1 = in_bracket(hi, hin); if (t1) hi = hin;
+        bool t2 = in_bracket(hi, mid); if (t2) hi = mid;
+        bool t3 = in_bracket(hi, lon); if (t3) hi = lon;
+        swap = s1 | s2 | s3 | t1 | t2 | t3;
+      }
     }
     bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
