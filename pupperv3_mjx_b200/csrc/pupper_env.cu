@@ -193,6 +193,13 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
     else if (i == 56) es.kp = v;
     else es.kd = v;
   }
+  // Contact slots are read (and multiplied by zero weights) by quads that have fewer contacts than the warp
+  // maximum, so they must never hold non-finite garbage: clear them once per launch.
+  {
+    float *cz = reinterpret_cast<float *>(es.con);
+    for (int i = k; i < (int)(sizeof(es.con) / 4); i += 4) cz[i] = 0.f;
+    if (k == 0) es.ncon = 0;
+  }
   __syncwarp(qm);
 
   LaneState L;

@@ -49,6 +49,22 @@ class Harness:
             rt.episode_field("steps")[:] = _dev(envs["steps"][None], dev, np.int32)
             rt.episode_field("first_obs")[:] = _dev(envs["first_obs"][:, :H * 36], dev)
 
+    def dump_state(self, idx=None):
+        """Device state -> oracle ENV_DTYPE rows (inverse of load_state; episode fields excluded)."""
+        from oracle import oracle
+        rt, n = self.rt, self.n
+        La, Li, H = self.cfg.n_latency, self.cfg.n_imu_latency, self.cfg.observation_history
+        e = np.zeros(n, dtype=oracle.ENV_DTYPE)
+        for f in FLOAT_FIELDS:
+            e[f] = rt.field(f).t().cpu().numpy().reshape(e[f].shape)
+        e["action_buffer"][:, :12 * La] = rt.field("action_buffer").t().cpu().numpy()
+        e["imu_buffer"][:, :6 * Li] = rt.field("imu_buffer").t().cpu().numpy()
+        e["rng"] = np.ascontiguousarray(rt.field("rng").t().cpu().numpy()).view(np.uint32)
+        e["last_contact"] = rt.field("last_contact")[0].cpu().numpy().astype(np.uint32)
+        e["step"] = rt.field("step")[0].cpu().numpy()
+        e["obs"][:, :H * 36] = rt.obs.cpu().numpy()
+        return e if idx is None else e[idx]
+
     def get(self, name):
         """Device value of an ENV_DTYPE field as numpy in the oracle's layout."""
         rt = self.rt
