@@ -165,6 +165,8 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    for t in range(args.settle):  # untimed pre-roll: robots dropped by reset land and episodes de-synchronise
+        rt.step(acts[t % n_act])
     for t in range(max(args.warmup, 3)):
         rt.step(acts[t % n_act])
     barrier()
@@ -237,7 +239,7 @@ def run_cuda(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[1]: flat ground, {n} envs/GPU, {'no' if args.no_dr else 'full'} domain randomisation, H={H}, "
                                f"fused episode/auto-reset, {'obstacle boxes, ' if args.obstacles else ''}5 substeps/step",
-                   "envs_per_gpu": n, "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
+                   "envs_per_gpu": n, "settle_steps": args.settle, "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
                    "timing": "mean of per-step CUDA event pairs on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
@@ -266,7 +268,7 @@ def run_cuda(args):
             r2.set_dr(sv)
             r2.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), en)).view(np.int32)).to(dev))
             a2 = [(torch.rand((en, 12), generator=g, device=dev) - 0.5) for _ in range(4)]
-            for t in range(5):
+            for t in range(args.settle + 5):
                 r2.step(a2[t % 4])
             torch.cuda.synchronize()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -291,6 +293,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (default: BASELINE configs[1])")
+    ap.add_argument("--settle", type=int, default=100, help="untimed pre-roll steps after reset (steady-state contacts)")
     ap.add_argument("--no-dr", action="store_true")
     ap.add_argument("--obstacles", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")

@@ -138,20 +138,25 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
   return new_rng;
 }
 
+#ifndef PUPPER_MIN_BLOCKS
+#define PUPPER_MIN_BLOCKS 2
+#endif
 template <bool RESET, bool DBG>
-__global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
+__global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
   {
     const uint32_t *src = reinterpret_cast<const uint32_t *>(p.model);
     uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.m);
-    for (int i = threadIdx.x; i < (int)(sizeof(PupperModelDesc) / 4); i += kBlock) dst[i] = src[i];
+#pragma unroll 4
+    for (int i = threadIdx.x; i < (int)(sizeof(PupperModelDesc) / 4); i += kBlock) dst[i] = __ldg(src + i);
     src = reinterpret_cast<const uint32_t *>(p.cfg);
     dst = reinterpret_cast<uint32_t *>(&sh.c);
-    for (int i = threadIdx.x; i < (int)(sizeof(PupperEnvCfg) / 4); i += kBlock) dst[i] = src[i];
+#pragma unroll 2
+    for (int i = threadIdx.x; i < (int)(sizeof(PupperEnvCfg) / 4); i += kBlock) dst[i] = __ldg(src + i);
     src = reinterpret_cast<const uint32_t *>(p.derived);
     dst = reinterpret_cast<uint32_t *>(&sh.d);
-    for (int i = threadIdx.x; i < (int)(sizeof(DerivedConsts) / 4); i += kBlock) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (int)(sizeof(DerivedConsts) / 4); i += kBlock) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, k = threadIdx.x & 3;
@@ -168,30 +173,30 @@ __global__ void __launch_bounds__(kBlock) env_kernel(const KParams p) {
   const int stride = p.st.stride;
 
   // ---- stage the per-env DR leaves (or the nominal values) in shared memory --------------------------
-  for (int i = k; i < 58; i += 4) {
-    float v;
-    if (p.has_dr) {
-      const int ds = p.dr.stride;
-      if (i < 13) v = p.dr.body_mass[(size_t)i * ds + e];
-      else if (i < 52) v = p.dr.body_inertia[(size_t)(i - 13) * ds + e];
-      else if (i < 55) v = p.dr.base_ipos[(size_t)(i - 52) * ds + e];
-      else if (i == 55) v = p.dr.friction[e];
-      else if (i == 56) v = p.dr.kp[e];
-      else v = p.dr.kd[e];
-    } else {
-      if (i < 13) v = m.body_mass[1 + i];
-      else if (i < 52) v = m.body_inertia[1 + (i - 13) / 3][(i - 13) % 3];
-      else if (i < 55) v = m.body_ipos[1][i - 52];
-      else if (i == 55) v = -1.f;
-      else if (i == 56) v = m.act_gain[0];
-      else v = -m.act_bias2[0];
+  // (two phases so the up-to-15 global loads of a lane are all in flight before the first is consumed)
+  {
+    float *ef = reinterpret_cast<float *>(&es);  // mass[13] inertia[39] ipos[3] friction kp kd are contiguous
+    float v[15];
+#pragma unroll
+    for (int t = 0; t < 15; t++) {
+      const int i = k + 4 * t;
+      v[t] = 0.f;
+      if (i < 58) {
+        if (p.has_dr) {
+          const int ds = p.dr.stride;
+          const float *src = i < 13 ? p.dr.body_mass + (size_t)i * ds
+                           : i < 52 ? p.dr.body_inertia + (size_t)(i - 13) * ds
+                           : i < 55 ? p.dr.base_ipos + (size_t)(i - 52) * ds
+                           : i == 55 ? p.dr.friction : (i == 56 ? p.dr.kp : p.dr.kd);
+          v[t] = __ldg(src + e);
+        } else {
+          v[t] = i < 13 ? m.body_mass[1 + i] : i < 52 ? m.body_inertia[1 + (i - 13) / 3][(i - 13) % 3]
+               : i < 55 ? m.body_ipos[1][i - 52] : i == 55 ? -1.f : (i == 56 ? m.act_gain[0] : -m.act_bias2[0]);
+        }
+      }
     }
-    if (i < 13) es.mass[i] = v;
-    else if (i < 52) es.inertia[i - 13] = v;
-    else if (i < 55) es.ipos[i - 52] = v;
-    else if (i == 55) es.friction = v;
-    else if (i == 56) es.kp = v;
-    else es.kd = v;
+#pragma unroll
+    for (int t = 0; t < 15; t++) if (k + 4 * t < 58) ef[k + 4 * t] = v[t];
   }
   // Contact slots are read (and multiplied by zero weights) by quads that have fewer contacts than the warp
   // maximum, so they must never hold non-finite garbage: clear them once per launch.
@@ -662,7 +667,7 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
   if (desc->abi_version != PUPPER_ABI_VERSION || cfg->abi_version != PUPPER_ABI_VERSION) return PUPPER_EVERSION;
   if (desc->iterations != 1 || cfg->threefry_partitionable != 1) return PUPPER_EUNSUPPORTED;
   if (desc->max_geom_pairs < 1 || desc->max_geom_pairs > 4) return PUPPER_EUNSUPPORTED;  // one narrow phase per lane
-  if (desc->max_contact_points < 1 || desc->max_contact_points > PUPPER_MAX_CON) return PUPPER_EUNSUPPORTED;
+  if (desc->max_contact_points < 1 || desc->max_contact_points > pupper::kMaxCon) return PUPPER_EUNSUPPORTED;
   if (desc->nbox < 0 || desc->nbox > PUPPER_MAX_BOX) return PUPPER_EUNSUPPORTED;
   if (cfg->observation_history < 1 || cfg->n_frames < 1) return PUPPER_EINVAL;
   if (cfg->n_latency < 1 || cfg->n_latency > PUPPER_MAX_LAT || cfg->n_imu_latency < 1 || cfg->n_imu_latency > PUPPER_MAX_LAT) return PUPPER_EINVAL;

@@ -25,7 +25,7 @@ namespace pupper {
 
 constexpr int kBlock = 128;           // threads per CTA
 constexpr int kEnvsPerBlock = kBlock / 4;
-constexpr int kMaxCon = 5 + 3;        // == PUPPER_MAX_CON
+constexpr int kMaxCon = 5;            // contact slots per env (max_contact_points <= 5)
 constexpr float kMinVal = 1e-15f, kMinImp = 1e-4f, kMaxImp = 0.9999f;
 constexpr float kInf = 3.0e38f;
 
@@ -75,6 +75,7 @@ struct BlockShared {
   DerivedConsts d;
   EnvShared env[kEnvsPerBlock];
   float rows[3 * kMaxCon * kBlock];  // contact-edge row scalars: [buffer][contact][thread]
+  float mat[45 * kBlock];            // per-lane copy of the mass matrix blocks: [element][thread]
 };
 
 __device__ __forceinline__ float qsum(float v, unsigned qm) {
@@ -113,6 +114,30 @@ __device__ __forceinline__ void tree_matvec(const TreeMat &A, const float xb[6],
     s = qsum(s, qm);
 #pragma unroll
     for (int i = 0; i < 6; i++) s = fmaf(A.B[i >= d ? tri(i, d) : tri(d, i)], xb[i], s);
+    yb[d] = s;
+  }
+}
+
+// Same product with the matrix read from shared memory (layout: element i of [B(21) | C(18) | D(6)] at sm[i*kBlock])
+__device__ __forceinline__ void tree_matvec_smem(const float *sm, const float xb[6], const float xl[3], float yb[6], float yl[3], unsigned qm) {
+  const float *B = sm, *C = sm + 21 * kBlock, *D = sm + 39 * kBlock;
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) s = fmaf(D[(i >= j ? tri(i, j) : tri(j, i)) * kBlock], xl[i], s);
+#pragma unroll
+    for (int d = 0; d < 6; d++) s = fmaf(C[(j * 6 + d) * kBlock], xb[d], s);
+    yl[j] = s;
+  }
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) s = fmaf(C[(j * 6 + d) * kBlock], xl[j], s);
+    s = qsum(s, qm);
+#pragma unroll
+    for (int i = 0; i < 6; i++) s = fmaf(B[(i >= d ? tri(i, d) : tri(d, i)) * kBlock], xb[i], s);
     yb[d] = s;
   }
 }
@@ -385,9 +410,19 @@ __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int 
 
 // Rare path: a leg-leg sphere contact couples two legs, so the Hessian is no longer arrow-shaped.
 // Gather the system on lane 0 of the quad and solve it densely (H holds M + diagonal row terms).
-__device__ __noinline__ void dense_newton_direction(const EnvShared &es, int ncon, int k, bool need, int qbase, const TreeMat &H,
-                                                    const float gb[6], const float gl[3], const S6 cd[3], const V3 ba[3], const V3 bo[3],
-                                                    const float *rowJ, float hb[6], float hl[3]) {
+struct DenseIO {  // memory-backed copy made only on the rare path, so the hot path's arrays stay in registers
+  TreeMat H;
+  float gb[6], gl[3];
+  S6 cd[3];
+  V3 ba[3], bo[3];
+  float hb[6], hl[3];
+};
+__device__ __noinline__ void dense_newton_direction(const EnvShared &es, int ncon, int k, bool need, int qbase, DenseIO &io, const float *rowJ) {
+  const TreeMat &H = io.H;
+  const float *gb = io.gb, *gl = io.gl;
+  const S6 *cd = io.cd;
+  const V3 *ba = io.ba, *bo = io.bo;
+  float *hb = io.hb, *hl = io.hl;
   const unsigned qm = 0xffffffffu;
   float Hd[18 * 18], Ld[18 * 18], xd[18], yd[18];
   float cdall[12][6];
@@ -937,7 +972,19 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 
   // forces, J^T f, gradient; Hessian additions
   float gb[6], gl[3];
-  TreeMat H = M;
+  // H is built in place in M's registers; the copy of M in shared memory serves the line search's M*search
+  {
+    float *msm = const_cast<float *>(sh.mat) + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 21; i++) msm[i * kBlock] = M.B[i];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int d = 0; d < 6; d++) msm[(21 + j * 6 + d) * kBlock] = M.C[j][d];
+#pragma unroll
+    for (int i = 0; i < 6; i++) msm[(39 + i) * kBlock] = M.D[i];
+  }
+  TreeMat &H = M;
   float Badd[21];
 #pragma unroll
   for (int i = 0; i < 21; i++) Badd[i] = 0.f;
@@ -1023,7 +1070,17 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   // Newton direction: search = -H^-1 grad
   float hb[6], hl[3];
   if (__any_sync(qm, any_ss)) {  // rare: some env of this warp has a leg-leg contact (H still holds M + diagonal terms there)
-    dense_newton_direction(es, ncon, k, any_ss, qbase, H, gb, gl, cd, ba, bo, rowJ, hb, hl);
+    DenseIO io;
+    io.H = H;
+#pragma unroll
+    for (int d = 0; d < 6; d++) { io.gb[d] = gb[d]; io.hb[d] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 3; j++) { io.gl[j] = gl[j]; io.hl[j] = 0.f; io.cd[j] = cd[j]; io.ba[j] = ba[j]; io.bo[j] = bo[j]; }
+    dense_newton_direction(es, ncon, k, any_ss, qbase, io, rowJ);
+#pragma unroll
+    for (int d = 0; d < 6; d++) hb[d] = io.hb[d];
+#pragma unroll
+    for (int j = 0; j < 3; j++) hl[j] = io.hl[j];
   }
   tree_factor(H, Badd, qm);
   {
@@ -1045,7 +1102,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   float alpha;
   {
     float mvb[6], mvl[3];
-    tree_matvec(M, hb, hl, mvb, mvl, qm);
+    tree_matvec_smem(sh.mat + threadIdx.x, hb, hl, mvb, mvl, qm);
     {
       float v1b[1][6], v1l[1][3];
 #pragma unroll

@@ -16,7 +16,7 @@ import torch
 from . import abi
 from .system import System
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpupper_env.so")
+_LIB_PATH = os.environ.get("PUPPER_ENV_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpupper_env.so")
 _lib: Optional[C.CDLL] = None
 
 
