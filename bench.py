@@ -54,7 +54,7 @@ def time_oracle(env, n, steps, warmup, use_dr, seed=0):
     import common
     from oracle import oracle
     from pupperv3_mjx_b200 import domain_randomization as dr, prng
-    O = oracle.Oracle(env.model_desc, env.env_cfg, "f32", n_threads=0)
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f32", n_threads=host_cores())  # torchrun pins OMP_NUM_THREADS=1: ask explicitly
     if use_dr:
         sys_v, _ = dr.domain_randomize(env.sys, prng.split(prng.PRNGKey(2), n))
         O.set_dr(common.dr_struct(sys_v))
@@ -176,7 +176,8 @@ def run_cuda(args):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     for t in range(args.steps):
-        flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
+        if not args.no_flush:
+            flush.zero_()  # L2 flush between timed iterations (outside the per-step event pair)
         ev[t][0].record()
         rt.step(acts[t % n_act])
         if world > 1 and (t + 1) % 100 == 0:
@@ -239,7 +240,7 @@ def run_cuda(args):
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"configs[1]: flat ground, {n} envs/GPU, {'no' if args.no_dr else 'full'} domain randomisation, H={H}, "
                                f"fused episode/auto-reset, {'obstacle boxes, ' if args.obstacles else ''}5 substeps/step",
-                   "envs_per_gpu": n, "settle_steps": args.settle, "l2": "flushed between timed steps (256 MB memset outside the event pairs)",
+                   "envs_per_gpu": n, "settle_steps": args.settle, "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between timed steps (256 MB memset outside the event pairs)",
                    "timing": "mean of per-step CUDA event pairs on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
@@ -295,6 +296,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU (default: BASELINE configs[1])")
     ap.add_argument("--settle", type=int, default=100, help="untimed pre-roll steps after reset (steady-state contacts)")
     ap.add_argument("--no-dr", action="store_true")
+    ap.add_argument("--no-flush", action="store_true", help="diagnostic: keep L2 warm between steps (not a bench number)")
     ap.add_argument("--obstacles", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time the 16384 / 65536 env batches (N=1)")

@@ -263,6 +263,24 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
     for (int i = k; i < PUPPER_NMETRIC; i += 4) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + i] = 0.f;
   } else {
     // ---- step (environment.py:348-483) ---------------------------------------------------------------------
+    // Everything the epilogue reads (lag buffers, obs history, bookkeeping, episode state) is cold in L2/DRAM and
+    // would be fetched one dependent round trip at a time after the physics: start those fetches now.
+    {
+      auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
+      const int Li = c.n_imu_latency;
+      for (int l = 0; l < Li; l++) { pf(p.st.imu_buffer + (size_t)(k * Li + l) * stride + e); if (k < 2) pf(p.st.imu_buffer + (size_t)((k + 4) * Li + l) * stride + e); }
+      for (int i = k * 32; i < H * PUPPER_OBS_DIM; i += 128) pf(p.st.obs + (size_t)e * H * PUPPER_OBS_DIM + i);
+#pragma unroll
+      for (int j = 0; j < 3; j++) pf(p.st.last_vel + (size_t)(3 * k + j) * stride + e);
+      pf(p.st.feet_air_time + (size_t)k * stride + e);
+      if (k == 0) { pf(p.st.last_contact + e); pf(p.st.step + e); }
+      if (p.has_ep) {
+        const int es_ = p.ep.stride;
+        for (int i = k; i < PUPPER_NMETRIC; i += 4) pf(p.ep.sum_metrics + (size_t)i * es_ + e);
+        if (k == 1) { pf(p.ep.episode_done + e); pf(p.ep.steps + e); }
+        if (k == 2) { pf(p.ep.sum_reward + e); pf(p.ep.length + e); }
+      }
+    }
     rng = make_uint2(p.st.rng[e], p.st.rng[stride + e]);
 #pragma unroll
     for (int i = 0; i < 7; i++) L.qb[i] = p.st.qpos[(size_t)i * stride + e];

@@ -23,7 +23,20 @@
 
 namespace pupper {
 
-constexpr int kBlock = 128;           // threads per CTA
+#ifndef PUPPER_BLOCK
+#define PUPPER_BLOCK 128
+#endif
+#ifndef PUPPER_PHASE_SYNC
+#define PUPPER_PHASE_SYNC 1
+#endif
+// Keeping a CTA's warps in step at phase boundaries lets them share instruction-cache fills: the kernel is
+// far larger than the I-cache and `no_instruction` is a top stall reason otherwise (profiles/r1_summary.md).
+#if PUPPER_PHASE_SYNC
+#define PHASE_SYNC() __syncthreads()
+#else
+#define PHASE_SYNC() ((void)0)
+#endif
+constexpr int kBlock = PUPPER_BLOCK;   // threads per CTA
 constexpr int kEnvsPerBlock = kBlock / 4;
 constexpr int kMaxCon = 5;            // contact slots per env (max_contact_points <= 5)
 constexpr float kMinVal = 1e-15f, kMinImp = 1e-4f, kMaxImp = 0.9999f;
@@ -517,6 +530,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   const int b0 = 2 + 3 * k;   // first body of this leg
   const float dt = m.timestep;
 
+  PHASE_SYNC();
   // ---- kinematics (A.2) ------------------------------------------------------------------------
   Q4 q1 = qnormalize(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]});
   L.qb[3] = q1.w; L.qb[4] = q1.x; L.qb[5] = q1.y; L.qb[6] = q1.z;
@@ -587,6 +601,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     C = mt < kMinVal ? xip_b : V3{pt.x / mt, pt.y / mt, pt.z / mt};
   }
 
+  PHASE_SYNC();
   // ---- cinert, cdof (A.3) -------------------------------------------------------------------------
   Inertia ci[3], cib;
 #pragma unroll
@@ -615,6 +630,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int i = 0; i < 3; i++) bo[i] = cross(ba[i], ob);
   }
 
+  PHASE_SYNC();
   // ---- velocities, RNE bias forces (A.7) -------------------------------------------------------------
   S6 cvb;  // base spatial velocity
   cvb.a = L.vb[3] * ba[0] + L.vb[4] * ba[1] + L.vb[5] * ba[2];
@@ -699,6 +715,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
   for (int d = 0; d < 6; d++) fs_b[d] = -m.dof_damping[d] * L.vb[d] - bias_b[d];
 
+  PHASE_SYNC();
   // ---- collision (A.5): keep only contacts that can act (dist < 0), at most max_contact_points ------
   __syncwarp(qm);  // sphere centres visible to the quad
   int ncon = 0;
@@ -872,6 +889,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
 
+  PHASE_SYNC();
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
   // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
   float *rowA = rows + threadIdx.x, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
@@ -906,6 +924,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     tree_solve(F, fs_b, fs_l, sb, sl, qm);
   }
 
+  PHASE_SYNC();
   // ---- Newton solver, one iteration (A.8) ------------------------------------------------------------------
   // cost at the warm start and at qacc_smooth.  (M qacc_smooth is taken as qfrc_smooth.)
   float Maw_b[6], Maw_l[3];
@@ -970,6 +989,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     lJ[j] = use_w ? jaw_l[j] : jas_l[j];
   }
 
+  PHASE_SYNC();
   // forces, J^T f, gradient; Hessian additions
   float gb[6], gl[3];
   // H is built in place in M's registers; the copy of M in shared memory serves the line search's M*search
@@ -1067,6 +1087,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int i = 0; i < 3; i++) gb[3 + i] = Mab[3 + i] - fs_b[3 + i] - (dot(ba[i], Sb.a) + dot(bo[i], Sb.l));
   }
 
+  PHASE_SYNC();
   // Newton direction: search = -H^-1 grad
   float hb[6], hl[3];
   if (__any_sync(qm, any_ss)) {  // rare: some env of this warp has a leg-leg contact (H still holds M + diagonal terms there)
@@ -1098,6 +1119,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
   for (int j = 0; j < 3; j++) hl[j] = -hl[j];
 
+  PHASE_SYNC();
   // ---- line search along `search` (A.8.3) ---------------------------------------------------------------------
   float alpha;
   {
