@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
     for (int j = 0; j < 3; j++) { L.ql[j] = c.init_q[7 + 3 * k + j]; L.vl[j] = 0.f; L.wl[j] = 0.f; L.ctrl[j] = 0.f; }
 #pragma unroll
     for (int d = 0; d < 6; d++) { L.vb[d] = 0.f; L.wb[d] = 0.f; }
-    forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, true, so, &dbg);  // pipeline_init = make_data + forward
+    forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, true, &dbg);
+    __syncwarp(qm);
+    so = load_stale(es, k);  // pipeline_init = make_data + forward
 #pragma unroll
     for (int d = 0; d < 6; d++) L.wb[d] = ab[d];
 #pragma unroll
@@ -271,7 +273,8 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
       for (int l = 0; l < Li; l++) { pf(p.st.imu_buffer + (size_t)(k * Li + l) * stride + e); if (k < 2) pf(p.st.imu_buffer + (size_t)((k + 4) * Li + l) * stride + e); }
       for (int i = k * 32; i < H * PUPPER_OBS_DIM; i += 128) pf(p.st.obs + (size_t)e * H * PUPPER_OBS_DIM + i);
 #pragma unroll
-      for (int j = 0; j < 3; j++) pf(p.st.last_vel + (size_t)(3 * k + j) * stride + e);
+      for (int j = 0; j < 3; j++) { pf(p.st.last_vel + (size_t)(3 * k + j) * stride + e); pf(p.st.last_act + (size_t)(3 * k + j) * stride + e); }
+      if (k < 3) { pf(p.st.command + (size_t)k * stride + e); pf(p.st.desired_world_z + (size_t)k * stride + e); }
       pf(p.st.feet_air_time + (size_t)k * stride + e);
       if (k == 0) { pf(p.st.last_contact + e); pf(p.st.step + e); }
       if (p.has_ep) {
@@ -292,10 +295,7 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
       L.ql[j] = p.st.qpos[(size_t)(7 + u) * stride + e];
       L.vl[j] = p.st.qvel[(size_t)(6 + u) * stride + e];
       L.wl[j] = p.st.qacc_warmstart[(size_t)(6 + u) * stride + e];
-      oc.last_act[j] = p.st.last_act[(size_t)u * stride + e];
     }
-#pragma unroll
-    for (int i = 0; i < 3; i++) { oc.command[i] = p.st.command[(size_t)i * stride + e]; oc.desired_z[i] = p.st.desired_world_z[(size_t)i * stride + e]; }
   }
 
   float act[3] = {0.f, 0.f, 0.f};
@@ -334,12 +334,14 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
       }
       float t = c.default_pose[u_] + lag * c.action_scale;
       L.ctrl[j] = fminf(fmaxf(t, c.joint_lower[u_]), c.joint_upper[u_]);
+      es.lv_act[u_] = act[j];
     }
+    if (k == 0) { es.lv_kick[0] = kick0; es.lv_kick[1] = kick1; es.lv_cmd_rng[0] = cmd_rng.x; es.lv_cmd_rng[1] = cmd_rng.y; }
     rng = K0;
     // S5 physics: n_frames x (forward ; semi-implicit Euler)
     const float dt = m.timestep;
     for (int f = 0; f < c.n_frames; f++) {
-      forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, f == c.n_frames - 1, so, &dbg);
+      forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, f == c.n_frames - 1, &dbg);
 #pragma unroll
       for (int d = 0; d < 6; d++) { L.wb[d] = ab[d]; L.vb[d] = fmaf(ab[d], dt, L.vb[d]); }
 #pragma unroll
@@ -352,8 +354,19 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
       Q4 qn = qnormalize(qmul(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]}, Q4{cs, w.x * sn, w.y * sn, w.z * sn}));
       L.qb[3] = qn.w; L.qb[4] = qn.x; L.qb[5] = qn.y; L.qb[6] = qn.z;
     }
+    __syncwarp(qm);
+    so = load_stale(es, k);
 #pragma unroll
-    for (int j = 0; j < 3; j++) oc.ql[j] = L.ql[j];
+    for (int j = 0; j < 3; j++) {
+      const int u = 3 * k + j;
+      oc.ql[j] = L.ql[j];
+      act[j] = es.lv_act[u];
+      oc.last_act[j] = p.st.last_act[(size_t)u * stride + e];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) { oc.command[i] = p.st.command[(size_t)i * stride + e]; oc.desired_z[i] = p.st.desired_world_z[(size_t)i * stride + e]; }
+    kick0 = es.lv_kick[0]; kick1 = es.lv_kick[1];
+    cmd_rng = make_uint2(es.lv_cmd_rng[0], es.lv_cmd_rng[1]);
     // S6 observation (reads the not-yet-updated last_act / command / desired_z)
     rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false, valid);
   }

@@ -68,7 +68,15 @@ struct ContactSlot {  // one ACTIVE contact (dist < 0) of an env, shared by the 
 };
 
 struct EnvShared {
-  float mass[13], inertia[39], ipos[3], friction, kp, kd;  // DR leaves (or nominal values)
+  float mass[13], inertia[39], ipos[3], friction, kp, kd;  // DR leaves (or nominal values); must stay first (staging loop)
+  // forward-pass quantities the env level reads after the last substep (the "stale" mix); parked
+  // here so that nothing of them occupies registers across the solver
+  float st_torso[16];    // pos3 rot4 ang3 vel3 com3
+  float st_leg[4][15];   // per leg: foot_site3 lower_pos3 lower_ang3 lower_vel3 frc3
+  float st_hits[2];      // knee / torso collision counters
+  // env-level values that must survive the physics loop
+  float lv_act[12], lv_kick[2];
+  uint32_t lv_cmd_rng[2];
   float sph[8][3];
   ContactSlot con[kMaxCon];
   int ncon;
@@ -357,10 +365,22 @@ struct StaleOut {
   float knee_hits, torso_hits;  // collision reward counters (whole env, replicated)
 };
 
+__device__ __forceinline__ StaleOut load_stale(const struct EnvShared &es, int k);
 struct DbgOut {  // only filled when DBG
   V3 pos[3]; Q4 rot[3]; V3 ang[3], vel[3];
   float qacc_b[6], qacc_l[3];
 };
+
+__device__ __forceinline__ StaleOut load_stale(const EnvShared &es, int k) {
+  StaleOut so;
+  const float *t = es.st_torso, *q = es.st_leg[k];
+  so.torso_pos = V3{t[0], t[1], t[2]}; so.torso_rot = Q4{t[3], t[4], t[5], t[6]};
+  so.torso_ang = V3{t[7], t[8], t[9]}; so.torso_vel = V3{t[10], t[11], t[12]}; so.com = V3{t[13], t[14], t[15]};
+  so.foot_site = V3{q[0], q[1], q[2]}; so.lower_pos = V3{q[3], q[4], q[5]}; so.lower_ang = V3{q[6], q[7], q[8]};
+  so.lower_vel = V3{q[9], q[10], q[11]}; so.frc[0] = q[12]; so.frc[1] = q[13]; so.frc[2] = q[14];
+  so.knee_hits = es.st_hits[0]; so.torso_hits = es.st_hits[1];
+  return so;
+}
 
 // Per-lane participation in contact c: bits 0-1 depth as body1 (-), bits 2-3 depth as body2 (+).
 __device__ __forceinline__ int participation(const ContactSlot &s, int k) {
@@ -525,7 +545,7 @@ __device__ __noinline__ void dense_newton_direction(const EnvShared &es, int nco
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, float *rows, LaneState &L, int k, unsigned qm, int qbase,
-                                     float ab[6], float al[3], bool want_stale, StaleOut &so, DbgOut *dbg) {
+                                     float ab[6], float al[3], bool want_stale, DbgOut *dbg) {
   const PupperModelDesc &m = sh.m;
   const int b0 = 2 + 3 * k;   // first body of this leg
   const float dt = m.timestep;
@@ -655,6 +675,23 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       pa = ca[j];
     }
   }
+  if (want_stale) {  // park what the env level needs from this forward pass (before the solver, to free registers)
+    if (k == 0) {
+      V3 tv = cvb.l + cross(cvb.a, p1 - C);  // xd.vel = lin - off x ang
+      float *t = es.st_torso;
+      t[0] = p1.x; t[1] = p1.y; t[2] = p1.z; t[3] = q1.w; t[4] = q1.x; t[5] = q1.y; t[6] = q1.z;
+      t[7] = cvb.a.x; t[8] = cvb.a.y; t[9] = cvb.a.z; t[10] = tv.x; t[11] = tv.y; t[12] = tv.z; t[13] = C.x; t[14] = C.y; t[15] = C.z;
+    }
+    V3 fs_ = pos[2] + rotate(V3{m.site_pos[1 + k][0], m.site_pos[1 + k][1], m.site_pos[1 + k][2]}, rot[2]);
+    V3 lv_ = cv[2].l + cross(cv[2].a, pos[2] - C);
+    float *q = es.st_leg[k];
+    q[0] = fs_.x; q[1] = fs_.y; q[2] = fs_.z; q[3] = pos[2].x; q[4] = pos[2].y; q[5] = pos[2].z;
+    q[6] = cv[2].a.x; q[7] = cv[2].a.y; q[8] = cv[2].a.z; q[9] = lv_.x; q[10] = lv_.y; q[11] = lv_.z;
+    if (DBG && dbg) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) { dbg->pos[j] = pos[j]; dbg->rot[j] = rot[j]; dbg->ang[j] = cv[j].a; dbg->vel[j] = cv[j].l + cross(cv[j].a, pos[j] - C); }
+    }
+  }
   float bias_l[3], bias_b[6];
   TreeMat M;
   {
@@ -714,6 +751,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   }
 #pragma unroll
   for (int d = 0; d < 6; d++) fs_b[d] = -m.dof_damping[d] * L.vb[d] - bias_b[d];
+  if (want_stale) { es.st_leg[k][12] = frc[0]; es.st_leg[k][13] = frc[1]; es.st_leg[k][14] = frc[2]; }
 
   PHASE_SYNC();
   // ---- collision (A.5): keep only contacts that can act (dist < 0), at most max_contact_points ------
@@ -889,6 +927,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
 
+  if (want_stale && k == 0) { es.st_hits[0] = knee_hits; es.st_hits[1] = torso_hits; }
   PHASE_SYNC();
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
   // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
@@ -1231,29 +1270,11 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
   for (int j = 0; j < 3; j++) al[j] = fmaf(alpha, hl[j], xl[j]);
 
-  if (want_stale) {
-    so.torso_pos = p1;
-    so.torso_rot = q1;
-    so.torso_ang = cvb.a;
-    so.torso_vel = cvb.l + cross(cvb.a, p1 - C);  // lin - off x ang
-    so.com = C;
-    so.foot_site = pos[2] + rotate(V3{m.site_pos[1 + k][0], m.site_pos[1 + k][1], m.site_pos[1 + k][2]}, rot[2]);
-    so.lower_pos = pos[2];
-    so.lower_ang = cv[2].a;
-    so.lower_vel = cv[2].l + cross(cv[2].a, pos[2] - C);
+  if (DBG && want_stale && dbg) {
 #pragma unroll
-    for (int j = 0; j < 3; j++) so.frc[j] = frc[j];
-    so.knee_hits = knee_hits;
-    so.torso_hits = torso_hits;
-    if (DBG && dbg) {
+    for (int j = 0; j < 3; j++) dbg->qacc_l[j] = al[j];
 #pragma unroll
-      for (int j = 0; j < 3; j++) {
-        dbg->pos[j] = pos[j]; dbg->rot[j] = rot[j]; dbg->ang[j] = cv[j].a; dbg->vel[j] = cv[j].l + cross(cv[j].a, pos[j] - C);
-        dbg->qacc_l[j] = al[j];
-      }
-#pragma unroll
-      for (int d = 0; d < 6; d++) dbg->qacc_b[d] = ab[d];
-    }
+    for (int d = 0; d < 6; d++) dbg->qacc_b[d] = ab[d];
   }
   es.ncon = ncon;
 }
