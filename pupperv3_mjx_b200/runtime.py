@@ -91,7 +91,7 @@ class PipelineStateView:
 
 class EnvRuntime:
     def __init__(self, model_desc: abi.PupperModelDesc, env_cfg: abi.PupperEnvCfg, n_envs: int, device: int = 0,
-                 episode: bool = False, debug: bool = False):
+                 episode: bool = False, debug: bool = False, guard_rows: int = 0):
         if not torch.cuda.is_available():
             raise PupperError("no CUDA device: the B200 kernel is the only implementation (no CPU fallback)")
         self.lib = load_library()
@@ -115,11 +115,16 @@ class EnvRuntime:
             self._fields[name] = t
             setattr(self.state, name, t.data_ptr())
         H = env_cfg.observation_history
-        self.obs = torch.zeros((self.n_envs, H * abi.OBS_DIM), dtype=torch.float32, device=self.device)
+        # env-major outputs; `guard_rows` extra rows (tests fill them with a sentinel to catch out-of-range writes)
+        self.guard_rows = int(guard_rows)
+        g = self.guard_rows
+        self._obs_full = torch.zeros((self.n_envs + g, H * abi.OBS_DIM), dtype=torch.float32, device=self.device)
+        self._reward_full = torch.zeros(self.n_envs + g, dtype=torch.float32, device=self.device)
+        self._done_full = torch.zeros(self.n_envs + g, dtype=torch.float32, device=self.device)
+        self._metrics_full = torch.zeros((self.n_envs + g, abi.NMETRIC), dtype=torch.float32, device=self.device)
+        self.obs, self.reward = self._obs_full[: self.n_envs], self._reward_full[: self.n_envs]
+        self.done, self.metrics = self._done_full[: self.n_envs], self._metrics_full[: self.n_envs]
         self.state.obs = self.obs.data_ptr()
-        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
-        self.done = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
-        self.metrics = torch.zeros((self.n_envs, abi.NMETRIC), dtype=torch.float32, device=self.device)
         self.out = abi.PupperStepOut()
         self.out.reward, self.out.done, self.out.metrics = self.reward.data_ptr(), self.done.data_ptr(), self.metrics.data_ptr()
         self.dbg: Dict[str, torch.Tensor] = {}

@@ -376,3 +376,72 @@ def test_public_api_reset_step_and_wrappers():
     from pupperv3_mjx_b200 import parallel
     rep = parallel.episode_report(tenv.episode_totals())
     assert rep["episodes"] >= 2 * n and 0 < rep["length"] <= 50
+
+
+def test_no_out_of_range_writes_with_ragged_batch():
+    """compute-sanitizer is closed on this pool, so out-of-range stores are hunted with sentinels: the SoA padding
+    columns (env index >= n_envs) and guard rows behind every env-major output must stay untouched."""
+    from pupperv3_mjx_b200 import runtime
+    env = common.make_env()
+    env.set_episode_params(5, 1)
+    n, SENT = 37, 12345.0
+    rt = runtime.EnvRuntime(env.model_desc, env.env_cfg, n, episode=True, debug=True, guard_rows=9)
+    for t in (rt._obs_full, rt._reward_full, rt._done_full, rt._metrics_full):
+        t[n:] = SENT
+    for name, t in list(rt._fields.items()) + [(k, v) for k, v in rt._ep_tensors.items() if k not in ("first_obs", "totals")]:
+        t[:, n:] = 77 if t.dtype == torch.int32 else SENT
+    keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
+    rt.reset(keys)
+    ndone = 0
+    for t in range(12):
+        rt.step(torch.from_numpy(common.actions(n, t)).cuda())
+        ndone += int(rt.done.sum().item())
+    torch.cuda.synchronize()
+    for t in (rt._obs_full, rt._reward_full, rt._done_full, rt._metrics_full):
+        assert bool((t[n:] == SENT).all())
+    for name, t in list(rt._fields.items()) + [(k, v) for k, v in rt._ep_tensors.items() if k not in ("first_obs", "totals")]:
+        assert bool((t[:, n:] == (77 if t.dtype == torch.int32 else SENT)).all()), name
+    assert torch.isfinite(rt.obs).all() and ndone >= 2 * n
+
+
+def test_cuda_graph_capture_replays_the_step():
+    """The ABI promises capture-safety (no sync, no allocation, caller-owned buffers): capture 4 steps, replay."""
+    env = common.make_env()
+    n = 256
+    keys = common.env_keys(n)
+    hA, hB = Harness(env, n), Harness(env, n)
+    hA.reset(keys); hB.reset(keys)
+    acts = [torch.from_numpy(common.actions(n, t)).cuda() for t in range(4)]
+    for a in acts:  # eager
+        hA.rt.step(a)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for a in acts:
+                hB.rt.step(a)
+    # capture records but does not execute: state B is still the reset state; one replay = 4 steps
+    g.replay()
+    torch.cuda.synchronize()
+    for f in ("qpos", "qvel", "obs", "reward", "rng"):
+        assert np.array_equal(hA.get(f), hB.get(f)), f
+
+
+def test_long_observation_history():
+    """H = 15 (the history length the reference's comment mentions, environment.py:338): roll + write-front parity."""
+    env = common.make_env(observation_history=15, **QUIET)
+    n = 64
+    h, O, _ = _pair(env, n)
+    keys = common.env_keys(n)
+    O.reset(keys); h.reset(keys)
+    np.testing.assert_allclose(h.get("obs"), O.obs(), atol=1e-6)
+    for t in range(18):
+        a = common.actions(n, t)
+        h.load_state(O.envs)
+        O.step(a); h.step(a)
+        got, ref = h.get("obs"), O.obs()
+        np.testing.assert_array_equal(got[:, 36:], ref[:, 36:].astype(np.float32))  # history slots: pure copies
+        assert np.median(np.abs(got[:, :36] - ref[:, :36]).max(1)) < 2e-3  # newest slot holds solver-dependent values (ang. velocity)
+    assert np.abs(O.obs()[:, -36:]).sum() > 0  # the oldest slot has been reached
