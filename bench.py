@@ -281,6 +281,26 @@ def run_cuda(args):
             extra[f"envs_{en}"] = {"value": en / (s0.elapsed_time(s1) / 50 * 1e-3), "unit": UNIT,
                                    "note": "flat ground, full DR, 50 back-to-back steps, state > L2 only at 65536"}
             del r2
+        # BASELINE configs[4] (substitute): rollout collection with a torch policy MLP in the loop, 8192 envs, CUDA graph
+        from pupperv3_mjx_b200 import rollout, wrappers
+        import functools
+        en, T = 8192, 20
+        env_r = make_env()
+        rand = functools.partial(dr.domain_randomize, rng=prng.split(prng.PRNGKey(2), en))
+        tenv = wrappers.wrap(env_r, episode_length=1000, randomization_fn=rand)
+        st = tenv.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), en)).view(np.int32)).to(dev))
+        col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env_r.observation_size), st, T, use_cuda_graph=True)
+        for _ in range(5):
+            col.collect()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(10):
+            col.collect()
+        s1.record()
+        torch.cuda.synchronize()
+        extra["rollout_8192"] = {"value": en * T * 10 / (s0.elapsed_time(s1) * 1e-3), "unit": UNIT,
+                                 "note": "unroll 20, torch MLP 72-256-128-128-128-12 (stand-in for the JAX policy) + env step, one CUDA graph per unroll"}
         line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:

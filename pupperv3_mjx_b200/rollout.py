@@ -1,0 +1,88 @@
+"""Rollout collection with the policy MLP in the loop (BASELINE configs[4]).
+
+The reference trains with Brax PPO (policy MLP in JAX).  JAX is unavailable here, so the policy is a torch MLP of
+the shape ``export.py`` describes (dense layers, observation normalisation folded into layer 0, tanh head) -- a
+labelled substitution.  One unroll = ``unroll_length`` x (policy forward [cuBLAS] + fused env step [this repo's
+kernel]); nothing synchronises with the host, so the whole unroll can be captured in a CUDA graph.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import utils
+from .environment import State
+
+
+class PolicyMLP(torch.nn.Module):
+    def __init__(self, layers: Sequence, device="cuda"):
+        super().__init__()
+        self.weights = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(W, dtype=torch.float32, device=device), requires_grad=False) for W, _, _ in layers])
+        self.biases = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(b, dtype=torch.float32, device=device), requires_grad=False) for _, b, _ in layers])
+        self.acts = [utils.activation_fn_map(a) for _, _, a in layers]
+
+    @classmethod
+    def random(cls, obs_size: int, hidden: Sequence[int] = (256, 128, 128, 128), action_size: int = 12, activation: str = "swish",
+               seed: int = 0, device="cuda") -> "PolicyMLP":
+        rng = np.random.default_rng(seed)
+        sizes = [obs_size, *hidden, action_size]
+        layers = []
+        for i in range(len(sizes) - 1):
+            W = rng.normal(0, 1.0 / np.sqrt(sizes[i]), size=(sizes[i], sizes[i + 1])).astype(np.float32)
+            layers.append((W, np.zeros(sizes[i + 1], np.float32), "tanh" if i == len(sizes) - 2 else activation))
+        return cls(layers, device)
+
+    @classmethod
+    def from_export(cls, policy_dict: Dict, device="cuda") -> "PolicyMLP":
+        from . import export
+        return cls(export.policy_from_dict(policy_dict), device)
+
+    @torch.no_grad()
+    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+        x = obs
+        for W, b, act in zip(self.weights, self.biases, self.acts):
+            x = act(torch.addmm(b, x, W))
+        return x
+
+
+class RolloutCollector:
+    """Preallocated [T, B, ...] buffers + optional CUDA-graph capture of one unroll."""
+
+    def __init__(self, tenv, policy: PolicyMLP, state: State, unroll_length: int, use_cuda_graph: bool = True):
+        self.tenv, self.policy, self.state, self.T = tenv, policy, state, int(unroll_length)
+        B, dev = state.obs.shape[0], state.obs.device
+        self.obs = torch.empty((self.T, B, state.obs.shape[1]), device=dev)
+        self.action = torch.empty((self.T, B, 12), device=dev)
+        self.reward = torch.empty((self.T, B), device=dev)
+        self.done = torch.empty((self.T, B), device=dev)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        if use_cuda_graph:
+            self._unroll()  # warm-up (allocator, cuBLAS handles) outside the capture
+            torch.cuda.synchronize()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s):
+                    self._unroll()
+            torch.cuda.current_stream().wait_stream(s)
+            self._graph = g
+
+    def _unroll(self):
+        rt = self.state.pipeline_state.runtime
+        for t in range(self.T):
+            self.obs[t].copy_(rt.obs)
+            self.action[t].copy_(self.policy(rt.obs))
+            rt.step(self.action[t])
+            self.reward[t].copy_(rt.reward)
+            self.done[t].copy_(rt.done)
+
+    def collect(self) -> Dict[str, torch.Tensor]:
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._unroll()
+        return {"obs": self.obs, "action": self.action, "reward": self.reward, "done": self.done}

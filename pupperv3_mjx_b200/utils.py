@@ -35,3 +35,41 @@ def sample_lagged_value(rng, buffer_newest_first: np.ndarray, new_value: np.ndar
     idx = int(prng.choice_index(np.asarray(rng, np.uint32), distribution))
     idx = min(idx, buf.shape[1] - 1)
     return buf[:, idx].copy(), buf
+
+
+# ---- model-file helpers (reference utils.py:145-199): host-side XML edits, run once ------------------------
+def set_mjx_custom_options(tree, max_contact_points: int, max_geom_pairs: int):
+    """Overwrite the ``max_contact_points`` / ``max_geom_pairs`` custom numerics; returns the tree, or ``None``
+    when the model has no ``<custom>`` element (the reference's behaviour)."""
+    custom = tree.getroot().find("custom")
+    if custom is None:
+        return None
+    wanted = {"max_contact_points": max_contact_points, "max_geom_pairs": max_geom_pairs}
+    for numeric in custom.findall("numeric"):
+        if numeric.get("name") in wanted:
+            numeric.set("data", str(wanted[numeric.get("name")]))
+    return tree
+
+
+def set_robot_starting_position(tree, starting_pos, starting_quat=None):
+    """Move ``base_link`` and the first 3 (7 with a quaternion) numbers of the ``home`` keyframe."""
+    body = tree.find(".//worldbody/body[@name='base_link']")
+    body.set("pos", " ".join(str(v) for v in starting_pos[:3]))
+    if starting_quat is not None:
+        body.set("quat", " ".join(str(v) for v in starting_quat[:4]))
+    key = tree.find(".//keyframe/key[@name='home']")
+    qpos = [float(v) for v in key.get("qpos").split()]
+    qpos[:3] = list(starting_pos[:3])
+    if starting_quat is not None:
+        qpos[3:7] = list(starting_quat[:4])
+    key.set("qpos", " ".join(str(v) for v in qpos))
+    return tree
+
+
+def activation_fn_map(name: str):
+    """Activation by name for the policy MLP (reference utils.activation_fn_map): torch callables; KeyError if unknown."""
+    import torch
+    import torch.nn.functional as F
+    table = {"relu": F.relu, "sigmoid": torch.sigmoid, "elu": F.elu, "tanh": torch.tanh, "swish": F.silu, "silu": F.silu,
+             "gelu": F.gelu, "softmax": lambda x: torch.softmax(x, dim=-1), "leaky_relu": F.leaky_relu, "linear": lambda x: x}
+    return table[name]
