@@ -234,7 +234,8 @@ def run_cuda(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     bytes_per_launch = b_alg(H) * n
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
-    flop_per_step = 1.55e5  # executed FP32 flop per env-step of this kernel (ncu r1, profiles/r1_summary.md)
+    flop_per_step = 1.54e5  # executed FP32 flop per env-step of this kernel (ncu, profiles/r1_summary.md)
+    traffic_4096 = 5.46e6  # dram__bytes_read+write per launch at 4096 envs from the ncu --set full capture (profiles/r1_summary.md)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -243,7 +244,7 @@ def run_cuda(args):
                    "envs_per_gpu": n, "settle_steps": args.settle, "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between timed steps (256 MB memset outside the event pairs)",
                    "timing": "mean of per-step CUDA event pairs on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
+                     "traffic": traffic_4096 if n == 4096 else None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
                      "note": "the step is FP32-pipe/latency bound, not HBM bound (DESIGN.md); see fp32"},
         "fp32": {"flop_per_env_step": flop_per_step, "achieved_tflops": flop_per_step * value / world / 1e12,
                  "peak_tflops": 74.4, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",

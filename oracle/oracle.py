@@ -61,10 +61,17 @@ def build(force: bool = False) -> str:
     """Compile ``liboracle.so`` with the committed Makefile if missing or stale."""
     src = [os.path.join(_HERE, f) for f in ("pupper_oracle.c", "oracle.h", "Makefile")]
     src.append(os.path.join(_HERE, "..", "include", "pupper_env.h"))
-    stale = force or not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
-    if stale:
-        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+    import hashlib
+    h = hashlib.sha256()
+    for s_ in src:
+        with open(s_, "rb") as f:
+            h.update(f.read())
+    stamp = _LIB_PATH + ".stamp"
+    stale = force or not os.path.exists(_LIB_PATH) or not os.path.exists(stamp) or open(stamp).read().strip() != h.hexdigest()
+    if stale:  # content-hash stamp: mtimes do not survive the copy to the GPU box
+        subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
+        with open(stamp, "w") as f:
+            f.write(h.hexdigest())
     return _LIB_PATH
 
 
