@@ -475,3 +475,31 @@ def test_rollout_collector_graph_matches_eager():
     torch.cuda.synchronize()
     for k in ("obs", "action", "reward", "done"):
         assert torch.equal(out[1][k], r2[k]), k
+
+
+def test_closed_loop_rollout_short_horizon_and_ensemble_statistics():
+    """Closed loop (no state injection): per-env agreement while the trajectories have not diverged yet, and
+    agreement of ensemble statistics (reward, height, termination rate) over a 300-step rollout afterwards."""
+    env = common.make_env()
+    env.set_episode_params(1000, 1)
+    n, T = 512, 300
+    h = Harness(env, n, episode=True)
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    keys = common.env_keys(n)
+    O.reset(keys); h.reset(keys)
+    rew_c, rew_o, z_c, z_o, dn_c, dn_o = [], [], [], [], 0, 0
+    for t in range(T):
+        a = common.actions(n, t, scale=0.3)
+        O.step(a, episode=True); h.step(a)
+        if t < 8:  # robots are still dropping / first touchdown: trajectories have not decorrelated
+            err = np.abs(h.get("qpos") - O.envs["qpos"]).max(1)
+            assert np.median(err) < (2e-4 if t < 5 else 2e-3), (t, np.median(err))
+            assert np.array_equal(h.get("rng"), O.envs["rng"])
+        rew_c.append(h.get("reward").mean()); rew_o.append(O.envs["reward"].mean())
+        z_c.append(h.get("qpos")[:, 2].mean()); z_o.append(O.envs["qpos"][:, 2].mean())
+        dn_c += h.get("done").sum(); dn_o += O.envs["done"].sum()
+    # PRNG streams never depend on the physics, so they stay identical for the whole rollout
+    assert np.array_equal(h.get("rng"), O.envs["rng"])
+    assert abs(np.mean(rew_c) - np.mean(rew_o)) < 0.05 * abs(np.mean(rew_o)) + 1e-4
+    assert abs(np.mean(z_c[50:]) - np.mean(z_o[50:])) < 0.01
+    assert abs(dn_c - dn_o) <= 0.25 * max(dn_o, 20)
