@@ -27,10 +27,11 @@ namespace pupper {
 #define PUPPER_BLOCK 128
 #endif
 #ifndef PUPPER_PHASE_SYNC
-#define PUPPER_PHASE_SYNC 1
+#define PUPPER_PHASE_SYNC 0
 #endif
-// Keeping a CTA's warps in step at phase boundaries lets them share instruction-cache fills: the kernel is
-// far larger than the I-cache and `no_instruction` is a top stall reason otherwise (profiles/r1_summary.md).
+// Experiment switch: CTA barriers at phase boundaries to keep a CTA's warps in step so they share
+// instruction-cache fills (`no_instruction` is a top stall reason, profiles/r1_summary.md).  Measured
+// A/B on B200: no difference at 4096 or 65,536 envs, so it is off.
 #if PUPPER_PHASE_SYNC
 #define PHASE_SYNC() __syncthreads()
 #else

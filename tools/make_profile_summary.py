@@ -108,7 +108,8 @@ L1TEX ("long_scoreboard": prologue/epilogue global accesses), shared memory ("sh
 | first correct kernel (unrolled contact loops, partial-mask shuffles, 39 k SASS instructions) | 6.6e6 | 1.13e7 |
 | rolled contact loops + smem row buffers + warp-uniform control flow/full-mask shuffles + fast div/sqrt (17 k instr.) | 1.57e7 | 4.18e7 |
 | + M staged in smem (H aliases M), dense-path arguments isolated, two-phase DR staging (spills 504 B -> 220 B) | 1.66e7 | 4.45e7 |
-| + stale forward-pass outputs and env-level values parked in smem (0 spills), epilogue prefetch, CTA phase barriers | 1.68e7 | 4.62e7 |
+| + stale forward-pass outputs and env-level values parked in smem (0 spills), epilogue prefetch | 1.68e7 | 4.62e7 |
+| CTA barriers at phase boundaries (I-cache sharing) on / off, same session | 1.57e7 / 1.57e7 | 4.56e7 / 4.56e7 |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
