@@ -236,6 +236,7 @@ def run_cuda(args):
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
     flop_per_step = 1.54e5  # executed FP32 flop per env-step of this kernel (ncu, profiles/r1_summary.md)
     traffic_4096 = 5.46e6  # dram__bytes_read+write per launch at 4096 envs from the ncu --set full capture (profiles/r1_summary.md)
+    ffma_peak = runtime.measure_ffma_tflops(local)  # measured FP32 denominator (MEASURED_PEAKS.json has none)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -247,8 +248,8 @@ def run_cuda(args):
                      "traffic": traffic_4096 if n == 4096 else None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
                      "note": "the step is FP32-pipe/latency bound, not HBM bound (DESIGN.md); see fp32"},
         "fp32": {"flop_per_env_step": flop_per_step, "achieved_tflops": flop_per_step * value / world / 1e12,
-                 "peak_tflops": 74.4, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz",
-                 "frac": flop_per_step * value / world / 1e12 / 74.4},
+                 "peak_tflops": ffma_peak, "peak_source": "measured in this run: FFMA probe kernel, 8 chains/thread, best of 5 (nominal 74.4)",
+                 "frac": flop_per_step * value / world / 1e12 / ffma_peak},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (H * abi.OBS_DIM + 2) * 4,
                 "steps": e2e_steps, "note": "PupperV3Env runtime step with pinned host action in, obs+reward+done out, sync each step"},

@@ -277,6 +277,11 @@ int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, Pupper
                 const float *action, PupperStepOut *out, PupperEpisode *episode,
                 pupper_stream_t stream);
 
+/* Measurement helper (bench.py): enqueues an FP32 FMA probe of blocks*256*iters*16 flop, to time with CUDA
+ * events for the measured FP32 roofline denominator. device_sink: any device float (never written). */
+int pupper_probe_ffma(int blocks, int iters, float *device_sink, pupper_stream_t stream);
+int pupper_sizeof(int which); /* 0..5: sizeof PupperModelDesc, EnvCfg, State, DR, StepOut, Episode (binding self-check) */
+
 /* Number of kernels the last pupper_step / pupper_reset call on this model enqueued. */
 int pupper_last_launch_count(const PupperModel *model);
 

@@ -632,6 +632,19 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KP
 
 }  // namespace pupper
 
+// FP32 roofline probe: 8 independent FMA chains per thread (2 flop each), no memory traffic in the loop.
+__global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float *sink) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {
+    a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+    a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+  }
+  float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123456.789f) sink[0] = r;  // never true; keeps the loop alive
+}
+
 // =====================================================================================================================
 // C ABI
 // =====================================================================================================================
@@ -795,13 +808,19 @@ static pupper::KParams make_params(const PupperModel *model, int n_envs, const P
 static bool wants_debug(const PupperStepOut *o) {
   return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc;
 }
+// the x / xd taps come as a group, and so do the two contact taps
+static bool debug_ok(const PupperStepOut *o) {
+  const bool any_x = o->dbg_x_pos || o->dbg_x_rot || o->dbg_xd_vel || o->dbg_xd_ang;
+  const bool all_x = o->dbg_x_pos && o->dbg_x_rot && o->dbg_xd_vel && o->dbg_xd_ang;
+  const bool con_ok = (o->dbg_contact_dist != nullptr) == (o->dbg_contact_geom != nullptr);
+  return (!any_x || all_x) && con_ok;
+}
 
 int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, const PupperDR *dr, PupperState *state, PupperStepOut *out,
                  PupperEpisode *episode, pupper_stream_t stream) {
   int rc = check_common(model, n_envs, dr, state, out, episode);
   if (rc != PUPPER_OK) return rc;
-  if (!keys) return PUPPER_EINVAL;
-  if (wants_debug(out) && (!out->dbg_x_pos || !out->dbg_x_rot || !out->dbg_xd_vel || !out->dbg_xd_ang)) { if (out->dbg_x_pos) return PUPPER_EINVAL; }
+  if (!keys || !debug_ok(out)) return PUPPER_EINVAL;
   pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -817,7 +836,7 @@ int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, Pupper
                 PupperEpisode *episode, pupper_stream_t stream) {
   int rc = check_common(model, n_envs, dr, state, out, episode);
   if (rc != PUPPER_OK) return rc;
-  if (!action) return PUPPER_EINVAL;
+  if (!action || !debug_ok(out)) return PUPPER_EINVAL;
   pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -827,6 +846,14 @@ int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, Pupper
   if (e != cudaSuccess) return cuda_fail(e, "pupper_step launch");
   const_cast<PupperModel *>(model)->last_launches = 1;
   return PUPPER_OK;
+}
+
+// Enqueues the FP32 probe: blocks x 256 threads x iters x 8 FMAs (flop = blocks*256*iters*16). Time it with events.
+int pupper_probe_ffma(int blocks, int iters, float *device_sink, pupper_stream_t stream) {
+  if (blocks <= 0 || iters <= 0 || !device_sink) return PUPPER_EINVAL;
+  ffma_probe_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, device_sink);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? PUPPER_OK : cuda_fail(e, "pupper_probe_ffma launch");
 }
 
 int pupper_last_launch_count(const PupperModel *model) { return model ? model->last_launches : PUPPER_EINVAL; }

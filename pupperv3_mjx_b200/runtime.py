@@ -44,6 +44,7 @@ def load_library() -> C.CDLL:
         lib.pupper_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pupper_last_launch_count.argtypes = [C.c_void_p]
         lib.pupper_state_rows.argtypes = [C.c_void_p, C.c_void_p]
+        lib.pupper_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut,
                                abi.PupperEpisode)):
             if lib.pupper_sizeof(i) != C.sizeof(s):
@@ -52,6 +53,27 @@ def load_library() -> C.CDLL:
             raise PupperError("ABI version mismatch")
         _lib = lib
     return _lib
+
+
+def measure_ffma_tflops(device: int = 0, iters: int = 1 << 16, reps: int = 5) -> float:
+    """Measured FP32 FMA throughput of the device (TFLOP/s): the compute-roofline denominator for the step kernel."""
+    lib = load_library()
+    dev = torch.device("cuda", device)
+    sink = torch.zeros(1, device=dev)
+    props = torch.cuda.get_device_properties(dev)
+    blocks = props.multi_processor_count * 8
+    best = 0.0
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        lib.pupper_probe_ffma(blocks, 1024, sink.data_ptr(), stream)  # warm-up
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _check(lib, lib.pupper_probe_ffma(blocks, iters, sink.data_ptr(), stream), "pupper_probe_ffma")
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = max(best, blocks * 256 * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
 
 
 def _check(lib, rc: int, what: str):
