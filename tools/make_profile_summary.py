@@ -110,6 +110,7 @@ L1TEX ("long_scoreboard": prologue/epilogue global accesses), shared memory ("sh
 | + M staged in smem (H aliases M), dense-path arguments isolated, two-phase DR staging (spills 504 B -> 220 B) | 1.66e7 | 4.45e7 |
 | + stale forward-pass outputs and env-level values parked in smem (0 spills), epilogue prefetch | 1.68e7 | 4.62e7 |
 | CTA barriers at phase boundaries (I-cache sharing) on / off, same session | 1.57e7 / 1.57e7 | 4.56e7 / 4.56e7 |
+| parking the lane's q/v/ctrl (22 floats) in smem during the Hessian build + line search (A/B, same session: 1.59e7 / 4.58e7 without) | 1.46e7 | 4.37e7 |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
