@@ -59,6 +59,11 @@ bench = json.loads(open(os.path.join(G, f"bench_{tag}.json")).read().strip().spl
 ref = json.loads(open(os.path.join(G, f"bench_{tag}_ref.json")).read().strip().splitlines()[-1])
 for src, dst in ((f"{tag}_launches.csv", f"{tag}_launches.csv"), (f"bench_{tag}.json", f"{tag}_bench_4096.json"), (f"bench_{tag}_ref.json", f"{tag}_bench_reference_arm.json")):
     open(os.path.join(P, dst), "w").write(open(os.path.join(G, src)).read())
+src_csv = os.path.join(G, f"{tag}_src_65536.csv")
+open(src_csv, "w").write(subprocess.run(["ncu", "-i", os.path.join(G, f"{tag}_prof_65536.ncu-rep"), "--page", "source", "--csv"], capture_output=True, text=True).stdout)
+phase = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "phase_hist.py"), src_csv, os.path.join(ROOT, "pupperv3_mjx_b200", "libpupper_env.so")],
+                       capture_output=True, text=True)
+phase_txt = phase.stdout if phase.returncode == 0 else "(library rebuilt since the capture: " + phase.stderr.strip().splitlines()[-1] + ")"
 md = f"""# Round 1 profile summary (B200, sm_100a, CUDA 12.9)
 
 Commands (through `gpurun`, one GPU; each ncu pass only after the same command exited 0 without ncu):
@@ -100,6 +105,14 @@ launch stays below the algorithmic 2,044 B x envs (part of the state is still L2
 re-reads and the HBM roofline fraction is <1 %; the FMA pipe is busy ~22 % at 65,536 envs. Stall mix: fixed-latency
 dependencies ("wait"), instruction fetch ("no_instruction": 17 k-instruction kernel, many branch targets),
 L1TEX ("long_scoreboard": prologue/epilogue global accesses), shared memory ("short_scoreboard").
+
+## Where the instructions and the stall samples go (65,536 envs; `tools/phase_hist.py`)
+
+```
+{phase_txt}```
+
+(Inlined helper code inherits the phase of the surrounding `forward()` code; "env-level" also holds the Euler update,
+the state load/store and the lag-buffer / observation / reward / episode code.)
 
 ## Experiments recorded this round (plain bench, CUDA events, env-steps/s)
 
