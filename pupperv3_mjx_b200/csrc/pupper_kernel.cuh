@@ -80,6 +80,7 @@ struct EnvShared {
   uint32_t lv_cmd_rng[2];
   float sph[8][3];
   ContactSlot con[kMaxCon];
+  float conW[kMaxCon][5];  // per contact: W00, W01, W02, W11, W22 of the contact-frame Hessian block
   int ncon;
 };
 
@@ -920,10 +921,12 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   const int ncon_w = __reduce_max_sync(qm, ncon);
   bool any_ss = false;
   float knee_hits = 0.f, torso_hits = 0.f;
+  int own_list = 0, own_count = 0;  // contacts in which this lane's leg takes part (3 bits per entry)
 #pragma unroll 1
   for (int c = 0; c < ncon; c++) {
     const ContactSlot &s = es.con[c];
     any_ss |= (s.code1 >= 0 && s.code2 >= 0);
+    if (participation(s, k)) { own_list |= c << (3 * own_count); own_count++; }
     if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
     if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
@@ -1086,35 +1089,55 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       S2 = fma6(s2w, w, S2);
       float wb_ = con_on ? (s.code2 >= 0 ? 1.f : 0.f) - (s.code1 >= 0 ? 1.f : 0.f) : 0.f;
       Sb = fma6(wb_, w, Sb);
-      // Hessian: Jc^T W Jc with W from the 4 edge weights (world-vs-leg contacts only; see the dense path)
-      float sd = (d0 + d1) + (d2 + d3);
-      int dep = dd2 | dd1;
-      if (sd > 0.f && !any_ss && dep) {
-        float W00 = sd, W01 = s.mu * (d0 - d1), W02 = s.mu * (d2 - d3), W11 = s.mu * s.mu * (d0 + d1), W22 = s.mu * s.mu * (d2 + d3);
-        float Jc[9][3], T[9][3];
+      // weights of the 3x3 contact-frame Hessian block W (from the 4 pyramid-edge weights), kept for the build below
+      if (k == 0 && con_on) {
+        float *wv = es.conW[c];
+        wv[0] = (d0 + d1) + (d2 + d3); wv[1] = s.mu * (d0 - d1); wv[2] = s.mu * (d2 - d3);
+        wv[3] = s.mu * s.mu * (d0 + d1); wv[4] = s.mu * s.mu * (d2 + d3);
+      }
+    }
+    // Hessian: H += Jc^T W Jc for world-vs-leg contacts.  Each lane walks ITS OWN contacts (the leg that touches
+    // has the cdofs), so the 4 lanes of a quad build different contacts at the same time; the trip count is the
+    // warp-wide maximum of contacts per leg (typically 1-2), not the number of contacts of the env.
+    __syncwarp(qm);
+    if (!__all_sync(qm, any_ss)) {
+      const int nown_w = __reduce_max_sync(qm, any_ss ? 0 : own_count);
+#pragma unroll 1
+      for (int i = 0; i < nown_w; i++) {
+        const int c = (own_list >> (3 * i)) & 7;
+        const ContactSlot &s = es.con[c];
+        const float *wv = es.conW[c];
+        const float W00 = wv[0];
+        if (i < own_count && !any_ss && W00 > 0.f) {
+          const float W01 = wv[1], W02 = wv[2], W11 = wv[3], W22 = wv[4];
+          const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+          const int pc = participation(s, k);
+          const int dep = (pc & 3) | ((pc >> 2) & 3);
+          float Jc[9][3], T[9][3];
 #pragma unroll
-        for (int d = 0; d < 9; d++) {
-          V3 col;
-          if (d < 3) col = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
-          else if (d < 6) col = bo[d - 3] + cross(ba[d - 3], r);
-          else col = (d - 6 <= dep) ? cd[d - 6].l + cross(cd[d - 6].a, r) : V3{0.f, 0.f, 0.f};
-          Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
-          Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
-          Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
-          T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
-          T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
-          T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
-        }
+          for (int d = 0; d < 9; d++) {
+            V3 col;
+            if (d < 3) col = V3{d == 0 ? 1.f : 0.f, d == 1 ? 1.f : 0.f, d == 2 ? 1.f : 0.f};
+            else if (d < 6) col = bo[d - 3] + cross(ba[d - 3], r);
+            else col = (d - 6 <= dep) ? cd[d - 6].l + cross(cd[d - 6].a, r) : V3{0.f, 0.f, 0.f};
+            Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
+            Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
+            Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
+            T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
+            T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
+            T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
+          }
 #pragma unroll
-        for (int i = 0; i < 6; i++)
+          for (int i2 = 0; i2 < 6; i2++)
 #pragma unroll
-          for (int j = 0; j <= i; j++) Badd[tri(i, j)] += T[i][0] * Jc[j][0] + T[i][1] * Jc[j][1] + T[i][2] * Jc[j][2];
+            for (int j = 0; j <= i2; j++) Badd[tri(i2, j)] += T[i2][0] * Jc[j][0] + T[i2][1] * Jc[j][1] + T[i2][2] * Jc[j][2];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
+          for (int j = 0; j < 3; j++) {
 #pragma unroll
-          for (int d = 0; d < 6; d++) H.C[j][d] += T[6 + j][0] * Jc[d][0] + T[6 + j][1] * Jc[d][1] + T[6 + j][2] * Jc[d][2];
+            for (int d = 0; d < 6; d++) H.C[j][d] += T[6 + j][0] * Jc[d][0] + T[6 + j][1] * Jc[d][1] + T[6 + j][2] * Jc[d][2];
 #pragma unroll
-          for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
+            for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
+          }
         }
       }
     }
