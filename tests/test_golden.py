@@ -21,3 +21,20 @@ def test_oracle_reproduces_golden_fixture():
         for f in ("qpos", "qvel", "reward", "done", "rng", "step", "last_contact", "command", "metrics"):
             np.testing.assert_array_equal(O.envs[f], g[f"{f}_{t}"], err_msg=f"{f} step {t}")
         np.testing.assert_array_equal(O.obs(), g[f"obs_{t}"])
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(not os.environ.get("MJX_GOLDEN"), reason="set MJX_GOLDEN=<npz from tools/dump_mjx_golden.py> (needs the real reference)")
+def test_oracle_against_real_mjx_golden():
+    """Pins the oracle itself against the real reference where one is available (tools/dump_mjx_golden.py)."""
+    g = np.load(os.environ["MJX_GOLDEN"])
+    env = common.make_env()
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f32")
+    O.reset(g["keys"])
+    for t in range(g["actions"].shape[0]):
+        O.step(g["actions"][t])
+        assert np.array_equal(O.envs["rng"], g[f"rng_{t}"])
+        assert np.median(np.abs(O.envs["qpos"] - g[f"qpos_{t}"]).max(1)) < 1e-4
+        assert np.median(np.abs(O.obs() - g[f"obs_{t}"]).max(1)) < 1e-3
