@@ -283,6 +283,29 @@ def run_cuda(args):
             extra[f"envs_{en}"] = {"value": en / (s0.elapsed_time(s1) / 50 * 1e-3), "unit": UNIT,
                                    "note": "flat ground, full DR, 50 back-to-back steps, state > L2 only at 65536"}
             del r2
+        # H = 15 at 65,536 envs: 380 MB of state + history per step, i.e. the one case that streams from HBM
+        import common as _c
+        env15 = _c.make_env(observation_history=15)
+        env15.set_episode_params(1000, 1)
+        en = 65536
+        r3 = runtime.EnvRuntime(env15.model_desc, env15.env_cfg, en, device=local, episode=True)
+        sv, _ = dr.domain_randomize(env15.sys, prng.split(prng.PRNGKey(2), en))
+        r3.set_dr(sv)
+        r3.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), en)).view(np.int32)).to(dev))
+        a3 = [(torch.rand((en, 12), generator=g, device=dev) - 0.5) for _ in range(4)]
+        for t in range(args.settle + 5):
+            r3.step(a3[t % 4])
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for t in range(50):
+            r3.step(a3[t % 4])
+        s1.record()
+        torch.cuda.synchronize()
+        v15 = en / (s0.elapsed_time(s1) / 50 * 1e-3)
+        extra["envs_65536_H15"] = {"value": v15, "unit": UNIT, "algorithmic_GBps": v15 * b_alg(15) / 1e9,
+                                   "note": f"observation_history=15: B_alg = {b_alg(15)} B/env-step, {en * b_alg(15) / 1e6:.0f} MB per step > L2"}
+        del r3
         # BASELINE configs[4] (substitute): rollout collection with a torch policy MLP in the loop, 8192 envs, CUDA graph
         from pupperv3_mjx_b200 import rollout, wrappers
         import functools
