@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 #include "pupper_kernel.cuh"
@@ -141,8 +142,13 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
 #ifndef PUPPER_MIN_BLOCKS
 #define PUPPER_MIN_BLOCKS 2
 #endif
+#ifdef PUPPER_NO_BOUNDS  // experiments: let -maxrregcount decide
+#define PUPPER_LB
+#else
+#define PUPPER_LB __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS)
+#endif
 template <bool RESET, bool DBG>
-__global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) env_kernel(const KParams p) {
+__global__ void PUPPER_LB env_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
   {
@@ -649,6 +655,7 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float *sink)
 // C ABI
 // =====================================================================================================================
 struct PupperModel {
+  int smem_bytes;  // dynamic shared memory per CTA (sizeof(BlockShared) + optional PUPPER_EXTRA_SMEM padding, an occupancy experiment knob)
   int device;
   PupperModelDesc *d_desc;
   PupperEnvCfg *d_cfg;
@@ -753,7 +760,9 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
   if (e == cudaSuccess) e = cudaMemcpy(m->d_desc, desc, sizeof(PupperModelDesc), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_cfg, cfg, sizeof(PupperEnvCfg), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(m->d_derived, &dc, sizeof(dc), cudaMemcpyHostToDevice);
-  const int smem = (int)sizeof(pupper::BlockShared);
+  int smem = (int)sizeof(pupper::BlockShared);
+  if (const char *pad = getenv("PUPPER_EXTRA_SMEM")) smem += atoi(pad);
+  m->smem_bytes = smem;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -824,8 +833,8 @@ int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, con
   pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
-  else pupper::env_kernel<true, false><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
+  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
+  else pupper::env_kernel<true, false><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_reset launch");
   const_cast<PupperModel *>(model)->last_launches = 1;
@@ -840,8 +849,8 @@ int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, Pupper
   pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
-  else pupper::env_kernel<false, false><<<grid, pupper::kBlock, sizeof(pupper::BlockShared), s>>>(p);
+  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
+  else pupper::env_kernel<false, false><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_step launch");
   const_cast<PupperModel *>(model)->last_launches = 1;

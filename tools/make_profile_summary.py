@@ -127,6 +127,10 @@ the state load/store and the lag-buffer / observation / reward / episode code.)
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
+| 96-thread CTAs x 3/SM at 224 registers (9 warps/SM, 124 B spills) | 1.59e7 | 3.72e7 |
+| 160-thread CTAs x 2/SM at 200 registers (10 warps/SM, 456 B spills) | 1.50e7 | 3.18e7 |
+| 64-thread CTAs x 4/SM (same 8 warps/SM) | 1.56e7 | 4.68e7 |
+| occupancy halved with shared-memory padding (1 CTA/SM = 4 warps/SM; `PUPPER_EXTRA_SMEM=60000`) | - | 3.06e7 (vs 4.75e7: 4 -> 8 warps/SM buys 1.55x) |
 | no L2 flush between steps (diagnostic, not a bench number) | 1.86e7 | 4.68e7 |
 """
 open(os.path.join(P, f"{tag}_summary.md"), "w").write(md)
