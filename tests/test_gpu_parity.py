@@ -546,3 +546,27 @@ def test_against_real_mjx_golden():
         assert np.median(np.abs(h.get("qpos") - g[f"qpos_{t}"]).max(1)) < 1e-4
         assert np.median(np.abs(h.get("obs") - g[f"obs_{t}"]).max(1)) < 1e-3
         assert (h.get("done") != g[f"done_{t}"]).mean() < 0.02
+
+
+def test_step_parity_without_imu_and_with_longer_latency_buffers():
+    """use_imu=False (identity rotation, zero angular velocity, environment.py:491-496) and 3-deep / 4-deep lag buffers."""
+    env = common.make_env(use_imu=False, latency_distribution=[0.2, 0.3, 0.5], imu_latency_distribution=[0.1, 0.2, 0.3, 0.4])
+    assert (env.env_cfg.n_latency, env.env_cfg.n_imu_latency, env.env_cfg.use_imu) == (3, 4, 0)
+    n = 128
+    h, O, _ = _pair(env, n)
+    keys = common.env_keys(n)
+    O.reset(keys); h.reset(keys)
+    np.testing.assert_allclose(h.get("obs"), O.obs(), atol=1e-6)
+    lags = set()
+    for t in range(25):
+        a = common.actions(n, t)
+        h.load_state(O.envs)
+        O.step(a, debug=True); h.step(a)
+        lags |= set(np.unique(O.debug["act_lag"]).tolist())
+        # lag picks and buffers are exact; without the IMU the first 6 obs entries carry no physics at all
+        np.testing.assert_array_equal(h.get("action_buffer"), O.envs["action_buffer"][:, :36].astype(np.float32))
+        np.testing.assert_allclose(h.get("imu_buffer"), O.envs["imu_buffer"][:, :24], atol=1e-6)
+        np.testing.assert_allclose(h.get("obs")[:, :12], O.obs()[:, :12], atol=1e-6)
+        assert np.array_equal(h.get("rng"), O.envs["rng"])
+        assert np.median(np.abs(h.get("obs") - O.obs()).max(1)) < 1e-3
+    assert lags == {0, 1, 2}
