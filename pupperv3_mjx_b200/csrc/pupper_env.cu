@@ -17,13 +17,31 @@ __device__ __forceinline__ uint2 qbcast2(uint2 v, int src, unsigned qm, int qbas
 
 // jax.random.choice index from the uniform draw u: searchsorted(cumsum(p), cumsum(p)[-1] * (1 - u))
 __device__ __forceinline__ int choice_from_u(float u, const float *p, int n) {
-  float cum[PUPPER_MAX_LAT];
+  float total = 0.f;
+  for (int i = 0; i < n; i++) total = __fadd_rn(total, p[i]);
+  const float r = __fmul_rn(total, __fsub_rn(1.0f, u));
   float acc = 0.f;
-  for (int i = 0; i < n; i++) { acc = __fadd_rn(acc, p[i]); cum[i] = acc; }
-  float r = __fmul_rn(acc, __fsub_rn(1.0f, u));
   int idx = 0;
-  for (int i = 0; i < n; i++) idx += (cum[i] < r) ? 1 : 0;
+  for (int i = 0; i < n; i++) { acc = __fadd_rn(acc, p[i]); idx += (acc < r) ? 1 : 0; }  // same running sums as cumsum
   return min(idx, n - 1);
+}
+
+// utils.sample_lagged_value on one row of a lag buffer held in global memory (row elements `stride` apart):
+// push `newest` at the front, return the element at column `pick` of the updated row.  All loads are issued before
+// the first store so they overlap (the compiler cannot reorder them itself: the pointers may alias).
+__device__ __forceinline__ float push_front_pick(float *row, int stride, int L, float newest, int pick, bool fresh, float fresh_value, bool valid) {
+  float old[PUPPER_MAX_LAT - 1];
+#pragma unroll
+  for (int l = 0; l < PUPPER_MAX_LAT - 1; l++) old[l] = (l < L - 1) ? (fresh ? fresh_value : row[(size_t)l * stride]) : 0.f;
+  float lag = newest;
+#pragma unroll
+  for (int l = 0; l < PUPPER_MAX_LAT - 1; l++) if (l + 1 == pick) lag = old[l];
+  if (valid) {
+    row[0] = newest;
+#pragma unroll
+    for (int l = 0; l < PUPPER_MAX_LAT - 1; l++) if (l < L - 1) row[(size_t)(l + 1) * stride] = old[l];
+  }
+  return lag;
 }
 
 // environment.py:246-272 (evaluated by one lane)
@@ -96,26 +114,26 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
   for (int t = 0; t < 2; t++) {
     int row = k + 4 * t;
     if (row < 6) {
-      float prev = 0.f;
+      float newest = 0.f;
 #pragma unroll
-      for (int i = 0; i < 6; i++) if (i == row) prev = imu[i];
-      float lag = prev;
-      for (int l = 0; l < Li; l++) {
-        float *ptr = p.st.imu_buffer + (size_t)(row * Li + l) * stride + e;
-        float old = zero_history ? (row == 5 ? -1.f : 0.f) : *ptr;
-        if (valid) *ptr = prev;
-        if (l == imu_idx) lag = prev;
-        prev = old;
-      }
-      lag_imu[t] = lag;
+      for (int i = 0; i < 6; i++) if (i == row) newest = imu[i];
+      lag_imu[t] = push_front_pick(p.st.imu_buffer + (size_t)(row * Li) * stride + e, stride, Li, newest, imu_idx, zero_history,
+                                   row == 5 ? -1.f : 0.f, valid);
     }
   }
 
   // history roll: slot h <- slot h-1 (each lane moves the entries i = k (mod 4))
   const int H = c.observation_history;
   float *obs = p.st.obs + (size_t)e * H * PUPPER_OBS_DIM;
-  for (int h = H - 1; h >= 1; h--)
-    for (int i = k; i < PUPPER_OBS_DIM; i += 4) if (valid) obs[h * PUPPER_OBS_DIM + i] = zero_history ? 0.f : obs[(h - 1) * PUPPER_OBS_DIM + i];
+  for (int h = H - 1; h >= 1; h--) {
+    float tmp[PUPPER_OBS_DIM / 4];
+#pragma unroll
+    for (int t = 0; t < PUPPER_OBS_DIM / 4; t++) tmp[t] = zero_history ? 0.f : obs[(h - 1) * PUPPER_OBS_DIM + k + 4 * t];
+    if (valid) {
+#pragma unroll
+      for (int t = 0; t < PUPPER_OBS_DIM / 4; t++) obs[h * PUPPER_OBS_DIM + k + 4 * t] = tmp[t];
+    }
+  }
   __syncwarp(qm);
   auto clip100 = [](float x) { return fminf(fmaxf(x, -100.f), 100.f); };
   // entries 0..11: imu(6), command(3), desired_z(3); this lane writes i = k, k+4, k+8
@@ -330,14 +348,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     for (int j = 0; j < 3; j++) {
       const int u_ = 3 * k + j;
       act[j] = p.action[(size_t)e * PUPPER_NU + u_];
-      float prev = act[j], lag = act[j];
-      for (int l = 0; l < La; l++) {
-        float *ptr = p.st.action_buffer + (size_t)(u_ * La + l) * stride + e;
-        float old = *ptr;
-        if (valid) *ptr = prev;
-        if (l == aidx) lag = prev;
-        prev = old;
-      }
+      float lag = push_front_pick(p.st.action_buffer + (size_t)(u_ * La) * stride + e, stride, La, act[j], aidx, false, 0.f, valid);
       float t = c.default_pose[u_] + lag * c.action_scale;
       L.ctrl[j] = fminf(fmaxf(t, c.joint_lower[u_]), c.joint_upper[u_]);
       es.lv_act[u_] = act[j];
@@ -596,14 +607,18 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     const float length = (p.ep.length[e] + (float)c.action_repeat) * keep;
     float ep_metric[5];  // this lane's metric rows i = k (mod 4)
 #pragma unroll
+    for (int t = 0; t < 5; t++) {  // loads first, so they overlap
+      int i = k + 4 * t;
+      ep_metric[t] = i < PUPPER_NMETRIC ? p.ep.sum_metrics[(size_t)i * es_ + e] : 0.f;
+    }
+#pragma unroll
     for (int t = 0; t < 5; t++) {
       int i = k + 4 * t;
-      ep_metric[t] = 0.f;
       if (i < PUPPER_NMETRIC) {
         float mv = total_dist;
 #pragma unroll
         for (int q = 0; q < PUPPER_NREWARD; q++) if (q + 1 == i) mv = rw[q];
-        float v = (p.ep.sum_metrics[(size_t)i * es_ + e] + mv) * keep;
+        float v = (ep_metric[t] + mv) * keep;
         if (valid) p.ep.sum_metrics[(size_t)i * es_ + e] = v;
         ep_metric[t] = v;
       }
@@ -621,12 +636,31 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
       }
     }
     if (fdone != 0.f) {  // AutoResetWrapper: restore the first pipeline state and first obs
-      for (int i = k; i < PUPPER_NQ; i += 4) if (valid) p.st.qpos[(size_t)i * stride + e] = p.ep.first_qpos[(size_t)i * es_ + e];
-      for (int i = k; i < PUPPER_NV; i += 4) {
-        if (valid) p.st.qvel[(size_t)i * stride + e] = p.ep.first_qvel[(size_t)i * es_ + e];
-        if (valid) p.st.qacc_warmstart[(size_t)i * stride + e] = p.ep.first_warmstart[(size_t)i * es_ + e];
+      // (loads batched ahead of the stores so they overlap)
+      float tq[5], tv[5], tw[5];
+#pragma unroll
+      for (int t = 0; t < 5; t++) {
+        const int i = k + 4 * t;
+        tq[t] = i < PUPPER_NQ ? p.ep.first_qpos[(size_t)i * es_ + e] : 0.f;
+        tv[t] = i < PUPPER_NV ? p.ep.first_qvel[(size_t)i * es_ + e] : 0.f;
+        tw[t] = i < PUPPER_NV ? p.ep.first_warmstart[(size_t)i * es_ + e] : 0.f;
       }
-      for (int i = k; i < H * PUPPER_OBS_DIM; i += 4) if (valid) p.st.obs[(size_t)e * H * PUPPER_OBS_DIM + i] = p.ep.first_obs[(size_t)e * H * PUPPER_OBS_DIM + i];
+#pragma unroll
+      for (int t = 0; t < 5; t++) {
+        const int i = k + 4 * t;
+        if (valid && i < PUPPER_NQ) p.st.qpos[(size_t)i * stride + e] = tq[t];
+        if (valid && i < PUPPER_NV) { p.st.qvel[(size_t)i * stride + e] = tv[t]; p.st.qacc_warmstart[(size_t)i * stride + e] = tw[t]; }
+      }
+      for (int h = 0; h < H; h++) {
+        float to[PUPPER_OBS_DIM / 4];
+        const size_t base = (size_t)e * H * PUPPER_OBS_DIM + (size_t)h * PUPPER_OBS_DIM + k;
+#pragma unroll
+        for (int t = 0; t < PUPPER_OBS_DIM / 4; t++) to[t] = p.ep.first_obs[base + 4 * t];
+        if (valid) {
+#pragma unroll
+          for (int t = 0; t < PUPPER_OBS_DIM / 4; t++) p.st.obs[base + 4 * t] = to[t];
+        }
+      }
     }
   }
 
