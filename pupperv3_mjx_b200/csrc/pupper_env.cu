@@ -784,6 +784,12 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
       dc.fric_D[d] = 1.f / R;
       dc.fric_rf[d] = dc.fric_loss[d] / dc.fric_D[d];
     }
+    {
+      int np = 0;
+      for (int a = 0; a < PUPPER_NSPHERE; a++)
+        for (int b = a + 1; b < PUPPER_NSPHERE; b++)
+          if (a / 2 != b / 2) dc.ss_pair[np++] = a | (b << 8);
+    }
     for (int b = 0; b < desc->nbox; b++)
       dc.box_rbound[b] = sqrtf(desc->box_size[b][0] * desc->box_size[b][0] + desc->box_size[b][1] * desc->box_size[b][1] + desc->box_size[b][2] * desc->box_size[b][2]);
   }

@@ -90,6 +90,7 @@ struct DerivedConsts {  // computed once on the host in pupper_model_create
   float fric_rf[PUPPER_NV];    // R * frictionloss: half-width of the quadratic zone
   float fric_b;                // velocity gain of aref
   float box_rbound[PUPPER_MAX_BOX];
+  int ss_pair[24];             // leg-leg sphere pairs in MJX order: a | b << 8  ({(a,b): a<b, a/2 != b/2}, lexicographic)
 };
 
 struct BlockShared {
@@ -407,7 +408,7 @@ __device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
 // memory at out[(n*kMaxCon + c)*kBlock].
 template <int N>
 __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int k, const S6 cd[3], const V3 ba[3], const V3 bo[3],
-                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int ncon_w, float *out) {
+                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int ncon_w, int part_all, float *out) {
   S6 W1[N];  // spatial velocity of this leg's link2 (depth 1) under v_n; link3 adds vl[2]*cd[2]
 #pragma unroll
   for (int n = 0; n < N; n++) {
@@ -420,7 +421,7 @@ __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int 
   for (int c = 0; c < ncon_w; c++) {  // ncon_w: warp-wide maximum, so the shuffles below stay convergent
     const ContactSlot &s = es.con[c];
     const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-    const int pc = c < ncon ? participation(s, k) : 0;
+    const int pc = (part_all >> (4 * c)) & 15;  // 0 for c >= ncon
     const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
     const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
     V3 pv[N];
@@ -821,12 +822,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       bool any_neg = false;
 #pragma unroll
       for (int i = 0; i < 6; i++) {
-        // pair p = 6k+i of the list {(a,b): a<b, a/2 != b/2} in lexicographic order
-        int p = 6 * k + i;
-        int a = p < 6 ? 0 : (p < 12 ? 1 : (p < 16 ? 2 : (p < 20 ? 3 : (p < 22 ? 4 : 5))));
-        int first = a < 2 ? 2 : (a < 4 ? 4 : 6);
-        int base = a == 0 ? 0 : (a == 1 ? 6 : (a == 2 ? 12 : (a == 3 ? 16 : (a == 4 ? 20 : 22))));
-        int b = first + (p - base);
+        const int ab = sh.d.ss_pair[6 * k + i];  // pair 6k+i of the MJX pair list
+        const int a = ab & 255, b = ab >> 8;
         V3 d = V3{es.sph[b][0] - es.sph[a][0], es.sph[b][1] - es.sph[a][1], es.sph[b][2] - es.sph[a][2]};
         pd[i] = sqrtf(dot(d, d)) - (m.sphere_radius[a] + m.sphere_radius[b]);
         pa[i] = a; pb[i] = b;
@@ -922,11 +919,16 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   bool any_ss = false;
   float knee_hits = 0.f, torso_hits = 0.f;
   int own_list = 0, own_count = 0;  // contacts in which this lane's leg takes part (3 bits per entry)
+  int part_all = 0;                 // participation code of this lane in every contact (4 bits per contact)
 #pragma unroll 1
   for (int c = 0; c < ncon; c++) {
     const ContactSlot &s = es.con[c];
     any_ss |= (s.code1 >= 0 && s.code2 >= 0);
-    if (participation(s, k)) { own_list |= c << (3 * own_count); own_count++; }
+    {
+      const int pc = participation(s, k);
+      part_all |= pc << (4 * c);
+      if (pc) { own_list |= c << (3 * own_count); own_count++; }
+    }
     if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
     if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
@@ -978,7 +980,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int d = 0; d < 6; d++) { v3b[0][d] = L.vb[d]; v3b[1][d] = L.wb[d]; v3b[2][d] = sb[d]; }
 #pragma unroll
     for (int j = 0; j < 3; j++) { v3l[0][j] = L.vl[j]; v3l[1][j] = L.wl[j]; v3l[2][j] = sl[j]; }
-    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, ncon_w, rowA);
+    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, ncon_w, part_all, rowA);
   }
   float cost_w, cost_s, gauss_w;
   float jaw_f[3], jaw_l[3], jas_f[3], jas_l[3];
@@ -1082,7 +1084,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
                 s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
       V3 r = V3{s.r[0], s.r[1], s.r[2]};
       S6 w = S6{cross(r, g), g};
-      const int pc = con_on ? participation(s, k) : 0;
+      const int pc = (part_all >> (4 * c)) & 15;  // 0 for c >= ncon
       int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
       float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
       S1 = fma6(s1w, w, S1);
@@ -1111,7 +1113,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         if (i < own_count && !any_ss && W00 > 0.f) {
           const float W01 = wv[1], W02 = wv[2], W11 = wv[3], W22 = wv[4];
           const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-          const int pc = participation(s, k);
+          const int pc = (part_all >> (4 * c)) & 15;
           const int dep = (pc & 3) | ((pc >> 2) & 3);
           float Jc[9][3], T[9][3];
 #pragma unroll
@@ -1194,7 +1196,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       for (int d = 0; d < 6; d++) v1b[0][d] = hb[d];
 #pragma unroll
       for (int j = 0; j < 3; j++) v1l[0][j] = hl[j];
-      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, ncon_w, rowA);  // jv of the contact-edge rows
+      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, ncon_w, part_all, rowA);  // jv of the contact-edge rows
     }
     float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];
     float q1l = 0.f, q2l = 0.f;
@@ -1212,18 +1214,21 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
     auto eval3 = [&](const float a[3], LSPoint out[3]) {
       float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
+      float b0 = 0.f, b1 = 0.f, b2 = 0.f;  // friction rows: quadratic-zone coefficients, common to the three points
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         if (fl[j] > 0.f) {
           const float ja = fJ[j], jv = hl[j];
           const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
-          const float ln = fl[j] * (-0.5f * rff[j] - ja), lp = fl[j] * (-0.5f * rff[j] + ja), lv = fl[j] * jv;
+          const float lv = fl[j] * jv, hr = -0.5f * rff[j];
+          // linear zones replace (qa, qb, qc) by (f(-R f/2 -+ ja), -+f jv, 0): add the difference where they apply
+          const float dn0 = fl[j] * (hr - ja) - qa, dn1 = -lv - qb, dp0 = fl[j] * (hr + ja) - qa, dp1 = lv - qb;
+          b0 += qa; b1 += qb; b2 += qc;
 #pragma unroll
           for (int p = 0; p < 3; p++) {
-            int z = fzone(fmaf(a[p], jv, ja), rff[j]);
-            s0[p] += z == 1 ? qa : (z == 2 ? ln : lp);
-            s1[p] += z == 1 ? qb : (z == 2 ? -lv : lv);
-            s2[p] += z == 1 ? qc : 0.f;
+            const float x = fmaf(a[p], jv, ja);
+            const bool neg = x <= -rff[j], lin = neg || (x >= rff[j]);
+            if (lin) { s0[p] += neg ? dn0 : dp0; s1[p] += neg ? dn1 : dp1; s2[p] -= qc; }
           }
         }
         if (lsign[j] != 0.f) {
@@ -1248,7 +1253,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
 #pragma unroll
       for (int p = 0; p < 3; p++) {
-        float t0 = gq0 + qsum(s0[p], qm), t1 = gq1 + qsum(s1[p], qm), t2 = gq2 + qsum(s2[p], qm);
+        float t0 = gq0 + qsum(s0[p] + b0, qm), t1 = gq1 + qsum(s1[p] + b1, qm), t2 = gq2 + qsum(s2[p] + b2, qm);
         out[p].alpha = a[p];
         out[p].cost = a[p] * a[p] * t2 + a[p] * t1 + t0;
         out[p].d0 = 2.f * a[p] * t2 + t1;
