@@ -124,6 +124,9 @@ the state load/store and the lag-buffer / observation / reward / episode code.)
 | + stale forward-pass outputs and env-level values parked in smem (0 spills), epilogue prefetch | 1.68e7 | 4.62e7 |
 | CTA barriers at phase boundaries (I-cache sharing) on / off, same session | 1.57e7 / 1.57e7 | 4.56e7 / 4.56e7 |
 | parking the lane's q/v/ctrl (22 floats) in smem during the Hessian build + line search (A/B, same session: 1.59e7 / 4.58e7 without) | 1.46e7 | 4.37e7 |
+| + Hessian build walks each lane's own contacts | 1.60e7 | 4.74e7 |
+| + epilogue loads batched ahead of stores (lag buffers, obs history, episode sums) | 1.66e7 | 4.99e7 |
+| + packed participation codes, tabulated leg-leg pairs, cheaper friction-row accumulation (final) | 1.71e7 | 4.94e7 |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
