@@ -1227,8 +1227,11 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
           for (int p = 0; p < 3; p++) {
             const float x = fmaf(a[p], jv, ja);
-            const bool neg = x <= -rff[j], lin = neg || (x >= rff[j]);
-            if (lin) { s0[p] += neg ? dn0 : dp0; s1[p] += neg ? dn1 : dp1; s2[p] -= qc; }
+            const bool neg = x <= -rff[j];
+            const float lin = (neg || (x >= rff[j])) ? 1.f : 0.f;  // branch-free: 0/1 weight of the correction
+            s0[p] = fmaf(lin, neg ? dn0 : dp0, s0[p]);
+            s1[p] = fmaf(lin, neg ? dn1 : dp1, s1[p]);
+            s2[p] = fmaf(-lin, qc, s2[p]);
           }
         }
         if (lsign[j] != 0.f) {
@@ -1236,8 +1239,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
           const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
 #pragma unroll
           for (int p = 0; p < 3; p++) {
-            bool on = fmaf(a[p], jv, ja) < 0.f;
-            s0[p] += on ? qa : 0.f; s1[p] += on ? qb : 0.f; s2[p] += on ? qc : 0.f;
+            const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
+            s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
           }
         }
       }
@@ -1247,8 +1250,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
 #pragma unroll
         for (int p = 0; p < 3; p++) {
-          bool on = fmaf(a[p], jv, ja) < 0.f;
-          s0[p] += on ? qa : 0.f; s1[p] += on ? qb : 0.f; s2[p] += on ? qc : 0.f;
+          const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
+          s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
         }
       }
 #pragma unroll
