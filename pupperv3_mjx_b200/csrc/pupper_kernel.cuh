@@ -988,18 +988,22 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     float cw = 0.f, cs = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      jaw_f[j] = 0.f; jas_f[j] = 0.f;
-      if (fl[j] > 0.f) {
-        float xw = L.wl[j] - fA[j], xs = sl[j] - fA[j];
+      // friction-loss row (Huber): 0.5 D x^2 inside |x| < R f, f (|x| - R f / 2) outside; a row without friction loss
+      // (fl = 0) has R f = 0 and contributes f * (...) = 0.  Branch-free on purpose (branches are costly here).
+      {
+        const float xw = L.wl[j] - fA[j], xs = sl[j] - fA[j];
         jaw_f[j] = xw; jas_f[j] = xs;
-        int zw = fzone(xw, rff[j]), zs = fzone(xs, rff[j]);
-        cw += zw == 1 ? 0.5f * fD[j] * xw * xw : (zw == 2 ? fl[j] * (-0.5f * rff[j] - xw) : fl[j] * (-0.5f * rff[j] + xw));
-        cs += zs == 1 ? 0.5f * fD[j] * xs * xs : (zs == 2 ? fl[j] * (-0.5f * rff[j] - xs) : fl[j] * (-0.5f * rff[j] + xs));
+        const float aw = fabsf(xw), as = fabsf(xs), hr = 0.5f * rff[j];
+        cw += aw >= rff[j] ? fl[j] * (aw - hr) : 0.5f * fD[j] * xw * xw;
+        cs += as >= rff[j] ? fl[j] * (as - hr) : 0.5f * fD[j] * xs * xs;
       }
-      float xw = lsign[j] * L.wl[j] - lA[j], xs = lsign[j] * sl[j] - lA[j];
-      jaw_l[j] = xw; jas_l[j] = xs;
-      if (xw < 0.f) cw += 0.5f * lD[j] * xw * xw;
-      if (xs < 0.f) cs += 0.5f * lD[j] * xs * xs;
+      {
+        const float xw = lsign[j] * L.wl[j] - lA[j], xs = lsign[j] * sl[j] - lA[j];
+        jaw_l[j] = xw; jas_l[j] = xs;
+        const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
+        cw = fmaf(0.5f * lD[j] * mw, mw, cw);
+        cs = fmaf(0.5f * lD[j] * ms, ms, cs);
+      }
     }
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {
@@ -1007,8 +1011,9 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       float aref = -s.b * rowA[c * kBlock] - s.kimp;
       float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
       rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;   // now Jaref at the warm start / at qacc_smooth
-      if (xw < 0.f) cw += 0.5f * s.D * xw * xw;
-      if (xs < 0.f) cs += 0.5f * s.D * xs * xs;
+      const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
+      cw = fmaf(0.5f * s.D * mw, mw, cw);
+      cs = fmaf(0.5f * s.D * ms, ms, cs);
     }
     float gw = 0.f;
 #pragma unroll
@@ -1057,14 +1062,15 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     float qc_l[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 3; j++) {
-      if (fl[j] > 0.f) {
-        int z = fzone(fJ[j], rff[j]);
-        qc_l[j] += z == 1 ? -fD[j] * fJ[j] : (z == 2 ? fl[j] : -fl[j]);
-        if (z == 1) H.D[tri(j, j)] += fD[j];
+      {  // friction-loss row: force -D x inside the quadratic zone (and the row enters H), -+f outside
+        const bool lin = fabsf(fJ[j]) >= rff[j];
+        qc_l[j] += lin ? -copysignf(fl[j], fJ[j]) : -fD[j] * fJ[j];
+        H.D[tri(j, j)] += lin ? 0.f : fD[j];
       }
-      if (lJ[j] < 0.f) {
-        qc_l[j] += lsign[j] * (-lD[j] * lJ[j]);
-        H.D[tri(j, j)] += lD[j];
+      {  // limit row: active when Jaref < 0
+        const float ml = fminf(lJ[j], 0.f);
+        qc_l[j] = fmaf(-lsign[j] * lD[j], ml, qc_l[j]);
+        H.D[tri(j, j)] += lJ[j] < 0.f ? lD[j] : 0.f;
       }
     }
     S6 S1 = S6{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, S2 = S1, Sb = S1;  // wrenches on link2 / link3 chains, base
@@ -1217,7 +1223,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       float b0 = 0.f, b1 = 0.f, b2 = 0.f;  // friction rows: quadratic-zone coefficients, common to the three points
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-        if (fl[j] > 0.f) {
+        {
           const float ja = fJ[j], jv = hl[j];
           const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
           const float lv = fl[j] * jv, hr = -0.5f * rff[j];
