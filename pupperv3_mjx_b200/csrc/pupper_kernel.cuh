@@ -399,8 +399,11 @@ __device__ __forceinline__ int fzone(float x, float rf) { return x <= -rf ? 2 : 
 struct LSPoint {
   float alpha, cost, d0, d1;
 };
+__device__ __forceinline__ LSPoint ls_select(bool c, const LSPoint &a, const LSPoint &b) {  // c ? a : b, field by field
+  return LSPoint{c ? a.alpha : b.alpha, c ? a.cost : b.cost, c ? a.d0 : b.d0, c ? a.d1 : b.d1};
+}
 __device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
-  return ((x.d0 < y.d0) && (y.d0 < 0.f)) || ((x.d0 > y.d0) && (y.d0 > 0.f));
+  return (((x.d0 < y.d0) & (y.d0 < 0.f)) | ((x.d0 > y.d0) & (y.d0 > 0.f))) != 0;  // bitwise: no short-circuit branches
 }
 
 // Row scalars of every active contact for this lane's pyramid edge: out[n][c] = (Jn + esgn*mu*Jt) . v_n
@@ -867,20 +870,18 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     // final cut: the max_contact_points smallest dist over [plane 0..7, box 8..11, sphere-sphere 12..15]
     const int maxc = m.max_contact_points;
     for (int r = 0; r < maxc; r++) {
-      float bk = kInf;
-      int bi = 0x7fffffff, bl = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        int id = i < 2 ? 2 * k + i : (i == 2 ? 8 + k : 12 + k);
-        if (cdist[i] < bk || (cdist[i] == bk && id < bi && cdist[i] < kInf)) { bk = cdist[i]; bi = id; bl = i; }
-      }
+      // local best of this lane's 4 candidates (ids grow with i, so the first minimum is also the lowest id)
+      const float bk = fminf(fminf(cdist[0], cdist[1]), fminf(cdist[2], cdist[3]));
+      const int bl = cdist[0] == bk ? 0 : (cdist[1] == bk ? 1 : (cdist[2] == bk ? 2 : 3));
+      const int bi = bk < kInf ? (bl < 2 ? 2 * k + bl : (bl == 2 ? 8 + k : 12 + k)) : 0x7fffffff;
       float mk = bk;
       int mi = bi;
 #pragma unroll
       for (int s = 1; s <= 2; s <<= 1) {
         float ok = __shfl_xor_sync(qm, mk, s);
         int oi = __shfl_xor_sync(qm, mi, s);
-        if (ok < mk || (ok == mk && oi < mi)) { mk = ok; mi = oi; }
+        const bool take = (ok < mk) | ((ok == mk) & (oi < mi));
+        mk = take ? ok : mk; mi = take ? oi : mi;
       }
       if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
       if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish slot r
@@ -1250,9 +1251,10 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
           }
         }
       }
-#pragma unroll 1
-      for (int c = 0; c < ncon; c++) {  // no shuffles inside: per-quad trip count is fine
-        const float ja = rowJ[c * kBlock], jv = rowA[c * kBlock], D = es.con[c].D;
+#pragma unroll
+      for (int c = 0; c < kMaxCon; c++) {  // unrolled and select-guarded: no loop or divergence branches
+        const bool con = c < ncon;
+        const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
         const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
 #pragma unroll
         for (int p = 0; p < 3; p++) {
@@ -1290,12 +1292,12 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
       } else if (ls_on) {
         const LSPoint lon = pt[0], hin = pt[1], mid = pt[2];
-        bool s1 = in_bracket(lo, lon); if (s1) lo = lon;
-        bool s2 = in_bracket(lo, mid); if (s2) lo = mid;
-        bool s3 = in_bracket(lo, hin); if (s3) lo = hin;
-        bool t1 = in_bracket(hi, hin); if (t1) hi = hin;
-        bool t2 = in_bracket(hi, mid); if (t2) hi = mid;
-        bool t3 = in_bracket(hi, lon); if (t3) hi = lon;
+        const bool s1 = in_bracket(lo, lon); lo = ls_select(s1, lon, lo);
+        const bool s2 = in_bracket(lo, mid); lo = ls_select(s2, mid, lo);
+        const bool s3 = in_bracket(lo, hin); lo = ls_select(s3, hin, lo);
+        const bool t1 = in_bracket(hi, hin); hi = ls_select(t1, hin, hi);
+        const bool t2 = in_bracket(hi, mid); hi = ls_select(t2, mid, hi);
+        const bool t3 = in_bracket(hi, lon); hi = ls_select(t3, lon, hi);
         swap = s1 | s2 | s3 | t1 | t2 | t3;
       }
     }
