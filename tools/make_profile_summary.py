@@ -126,7 +126,10 @@ the state load/store and the lag-buffer / observation / reward / episode code.)
 | parking the lane's q/v/ctrl (22 floats) in smem during the Hessian build + line search (A/B, same session: 1.59e7 / 4.58e7 without) | 1.46e7 | 4.37e7 |
 | + Hessian build walks each lane's own contacts | 1.60e7 | 4.74e7 |
 | + epilogue loads batched ahead of stores (lag buffers, obs history, episode sums) | 1.66e7 | 4.99e7 |
-| + packed participation codes, tabulated leg-leg pairs, cheaper friction-row accumulation (final) | 1.71e7 | 4.94e7 |
+| + packed participation codes, tabulated leg-leg pairs, cheaper friction-row accumulation | 1.71e7 | 4.94e7 |
+| + branch-free row accumulation in the line search | 1.86e7 | 5.42e7 |
+| + branch-free cost evaluation / force rows | 1.89e7 | 5.52e7 |
+| + branch-free bracket updates and contact selection, unrolled select-guarded contact rows (final) | 1.95e7 | 5.67e7 |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
