@@ -367,7 +367,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
       V3 w = V3{L.vb[3], L.vb[4], L.vb[5]};
       float nrm = normalize3(w);
       float sn, cs;
-      sincosf(dt * nrm * 0.5f, &sn, &cs);
+      sincos_small(dt * nrm * 0.5f, &sn, &cs);
       Q4 qn = qnormalize(qmul(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]}, Q4{cs, w.x * sn, w.y * sn, w.z * sn}));
       L.qb[3] = qn.w; L.qb[4] = qn.x; L.qb[5] = qn.y; L.qb[6] = qn.z;
     }

@@ -243,6 +243,12 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
   xl[0] = (w0 - F.D[1] * xl[1] - F.D[3] * xl[2]) / F.D[0];
 }
 
+__device__ __noinline__ float impedance_curve_generic(float x, float mid, float power) {
+  const float ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
+  const float ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+  return x < mid ? ia : ib;
+}
+
 // solref/solimp -> (k, b, imp) at constraint violation `pos`
 __device__ __forceinline__ void kbi(const float *solref, const float *solimp, float timestep, float pos, float &k, float &b, float &imp) {
   float timeconst = fmaxf(solref[0], 2.f * timestep), dampratio = solref[1];
@@ -253,15 +259,14 @@ __device__ __forceinline__ void kbi(const float *solref, const float *solimp, fl
   if (solref[0] <= 0.f) k = -solref[0] / (dmax * dmax);
   if (solref[1] <= 0.f) b = -solref[1] / dmax;
   float x = fabsf(pos) / width;
-  float ia, ib;
-  if (power == 2.f) {
-    ia = (1.f / mid) * (x * x);
-    ib = 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
+  float y;
+  if (power == 2.f) {  // the model's setting; the general power law lives out of line to keep the hot path compact
+    const float ia = (1.f / mid) * (x * x);
+    const float ib = 1.f - (1.f / (1.f - mid)) * ((1.f - x) * (1.f - x));
+    y = x < mid ? ia : ib;
   } else {
-    ia = (1.f / powf(mid, power - 1.f)) * powf(x, power);
-    ib = 1.f - (1.f / powf(1.f - mid, power - 1.f)) * powf(1.f - x, power);
+    y = impedance_curve_generic(x, mid, power);
   }
-  float y = x < mid ? ia : ib;
   float im = dmin + y * (dmax - dmin);
   im = fminf(fmaxf(im, dmin), dmax);
   if (x > 1.f) im = dmax;
@@ -575,7 +580,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       Q4 q = qmul(pq, Q4{m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
       axis[j] = rotate(V3{0.f, 0.f, 1.f}, q);
       float sn, cs;
-      sincosf(L.ql[j] * 0.5f, &sn, &cs);
+      sincos_small(L.ql[j] * 0.5f, &sn, &cs);
       rot[j] = qmul(q, Q4{cs, 0.f, 0.f, sn});
       xip[j] = pos[j] + rotate(V3{m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]}, rot[j]);
       M3 Ri = qmat(qmul(rot[j], Q4{m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]}));

@@ -99,6 +99,29 @@ __device__ __forceinline__ float brax_norm(V3 v) {
   return sqrtf(dot(v, v));
 }
 
+// Branch-free sin/cos for moderate arguments (|x| < ~1e3: joint half-angles, integration half-angles): three-term
+// Cody-Waite reduction to [-pi/4, pi/4] and minimax polynomials, ~1 ulp.  The CUDA library version inlines a
+// large-argument slow path at every call site, which bloats the straight-line hot path for nothing here.
+__device__ __forceinline__ void sincos_small(float x, float *sn, float *cs) {
+  const float k = rintf(x * 0.636619772f);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  const float r2 = r * r;
+  float s = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  s = fmaf(s, r2, -1.6666654611e-1f);
+  s = fmaf(s * r2, r, r);
+  float c = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  c = fmaf(c, r2, 4.166664568298827e-2f);
+  c = fmaf(c, r2, -0.5f);
+  c = fmaf(c, r2, 1.0f);
+  const int q = (int)k;
+  const bool swap = q & 1;
+  const float ss = swap ? c : s, cc = swap ? s : c;
+  *sn = (q & 2) ? -ss : ss;
+  *cs = ((q + 1) & 2) ? -cc : cc;
+}
+
 // ---- jax 0.5.0 threefry2x32 (partitionable derivation), SURVEY.md A.11 ------------------------------
 __device__ __forceinline__ uint2 threefry2x32(uint2 key, uint32_t c0, uint32_t c1) {
   const uint32_t ks0 = key.x, ks1 = key.y, ks2 = key.x ^ key.y ^ 0x1BD11BDAu;
