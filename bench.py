@@ -76,6 +76,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, False
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.ready = threading.Event()  # set once NVML is initialised, so short timed regions still get samples
 
     def run(self):
         try:
@@ -85,6 +86,7 @@ class ClockSampler(threading.Thread):
             self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
             names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                      "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            self.ready.set()
             while not self.stop_flag:
                 self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 try:
@@ -94,9 +96,10 @@ class ClockSampler(threading.Thread):
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.01)
+                time.sleep(0.002)
         except Exception as e:  # NVML unavailable: report that instead of inventing numbers
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+            self.ready.set()
 
     def result(self):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
@@ -173,6 +176,7 @@ def run_cuda(args):
     launches0 = rt.launches
     sampler = ClockSampler(local)
     sampler.start()
+    sampler.ready.wait(timeout=10)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     wall0 = time.perf_counter()
     for t in range(args.steps):
@@ -188,7 +192,8 @@ def run_cuda(args):
     wall = time.perf_counter() - wall0
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    per_step = np.array([a.elapsed_time(b) for a, b in ev])
+    kernel_ms = float(np.mean(per_step))
     tt = torch.tensor([kernel_ms], device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -254,6 +259,8 @@ def run_cuda(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (H * abi.OBS_DIM + 2) * 4,
                 "steps": e2e_steps, "note": "PupperV3Env runtime step with pinned host action in, obs+reward+done out, sync each step"},
         "gpu_launches": launches,
+        "ms_per_step_quantiles": {"p50": float(np.quantile(per_step, 0.5)), "p90": float(np.quantile(per_step, 0.9)),
+                                  "max": float(per_step.max()), "note": "rank 0; steps in which an env takes a rare solver path run longer"},
         "wall_s_timed_region": wall,
     }
     if world == 1 and not args.skip_cpu:

@@ -66,6 +66,7 @@ struct ContactSlot {  // one ACTIVE contact (dist < 0) of an env, shared by the 
   float dist;
   int code1, code2;  // leg*4 + depth (1: link2 / knee sphere, 2: link3 / foot sphere) or -1 for the world
   int s1, s2;        // sphere indices (or -1) for the collision rewards
+  int ty, box;       // pair type (0 plane-sphere, 1 sphere-box, 2 sphere-sphere) and box index
 };
 
 struct EnvShared {
@@ -889,56 +890,73 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         mk = take ? ok : mk; mi = take ? oi : mi;
       }
       if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
-      if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish slot r
+      if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish the raw candidate in slot r
         ContactSlot &s = es.con[r];
         V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
         int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
-        const int bxi = cbox;
 #pragma unroll
         for (int i = 0; i < 4; i++) if (i == bl) { pp = cpos[i]; nn = cn[i]; c1 = ccode1[i]; c2 = ccode2[i]; s1 = cs1[i]; s2 = cs2[i]; ty = ctype[i]; cdist[i] = kInf; }
         s.r[0] = pp.x - C.x; s.r[1] = pp.y - C.y; s.r[2] = pp.z - C.z;
-        make_frame(nn, s.frame);
-        // geom friction: one DR draw for every geom (es.friction >= 0) or the model's per-geom values
-        const bool drf = es.friction >= 0.f;
-        float f1 = s1 >= 0 ? (drf ? es.friction : m.sphere_friction[s1]) : (drf ? es.friction : m.floor_friction);
-        float f2 = s2 >= 0 ? (drf ? es.friction : m.sphere_friction[s2]) : (ty == 1 ? (drf ? es.friction : m.box_friction[bxi]) : (drf ? es.friction : m.floor_friction));
-        if (ty == 0) f1 = drf ? es.friction : m.floor_friction;
-        float mu = fmaxf(f1, f2);
-        float w1 = c1 >= 0 ? m.body_invweight0[2 + 3 * (c1 >> 2) + (c1 & 3)] : 0.f;
-        float w2 = c2 >= 0 ? m.body_invweight0[2 + 3 * (c2 >> 2) + (c2 & 3)] : 0.f;
-        float t = w1 + w2;
-        float invw = t + mu * mu * t;
-        invw = invw * 2.f * mu * mu / m.impratio;
-        const float *solref = ty == 0 ? m.plane_sphere_solref : (ty == 1 ? m.sphere_box_solref : m.sphere_sphere_solref);
-        const float *solimp = ty == 0 ? m.plane_sphere_solimp : (ty == 1 ? m.sphere_box_solimp : m.sphere_sphere_solimp);
-        float kk, bb, imp;
-        kbi(solref, solimp, dt, bk, kk, bb, imp);
-        float Rr = fmaxf(invw * (1.f - imp) / imp, kMinVal);
-        s.mu = mu; s.D = 1.f / Rr; s.b = bb; s.kimp = kk * imp * bk; s.dist = bk;
-        s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2;
+        s.frame[0] = nn.x; s.frame[1] = nn.y; s.frame[2] = nn.z;
+        s.dist = bk;
+        s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2; s.ty = ty; s.box = cbox;
       }
       if (mk < 0.f) ncon = r + 1;
     }
   }
-  __syncwarp(qm);  // contact slots visible to the quad
+  __syncwarp(qm);  // raw contact slots visible to the quad
   const int ncon_w = __reduce_max_sync(qm, ncon);
-  bool any_ss = false;
+  // Complete the slots in parallel: lane k derives frame, friction, impedance and row weight of slot k (then k + 4),
+  // instead of the winner lane doing it alone inside the selection loop.
+#pragma unroll 1
+  for (int c0 = 0; c0 < ncon_w; c0 += 4) {  // warp-uniform trip count (<= 2)
+    const int c = c0 + k;
+    if (c < ncon) {
+      ContactSlot &s = es.con[c];
+      const int c1 = s.code1, c2 = s.code2, s1 = s.s1, s2 = s.s2, ty = s.ty, bxi = s.box;
+      const float bk = s.dist;
+      make_frame(V3{s.frame[0], s.frame[1], s.frame[2]}, s.frame);
+      // geom friction: one DR draw for every geom (es.friction >= 0) or the model's per-geom values
+      const bool drf = es.friction >= 0.f;
+      float f1 = s1 >= 0 ? (drf ? es.friction : m.sphere_friction[s1]) : (drf ? es.friction : m.floor_friction);
+      float f2 = s2 >= 0 ? (drf ? es.friction : m.sphere_friction[s2]) : (ty == 1 ? (drf ? es.friction : m.box_friction[bxi]) : (drf ? es.friction : m.floor_friction));
+      if (ty == 0) f1 = drf ? es.friction : m.floor_friction;
+      float mu = fmaxf(f1, f2);
+      float w1 = c1 >= 0 ? m.body_invweight0[2 + 3 * (c1 >> 2) + (c1 & 3)] : 0.f;
+      float w2 = c2 >= 0 ? m.body_invweight0[2 + 3 * (c2 >> 2) + (c2 & 3)] : 0.f;
+      float t = w1 + w2;
+      float invw = t + mu * mu * t;
+      invw = invw * 2.f * mu * mu / m.impratio;
+      const float *solref = ty == 0 ? m.plane_sphere_solref : (ty == 1 ? m.sphere_box_solref : m.sphere_sphere_solref);
+      const float *solimp = ty == 0 ? m.plane_sphere_solimp : (ty == 1 ? m.sphere_box_solimp : m.sphere_sphere_solimp);
+      float kk, bb, imp;
+      kbi(solref, solimp, dt, bk, kk, bb, imp);
+      float Rr = fmaxf(invw * (1.f - imp) / imp, kMinVal);
+      s.mu = mu; s.D = 1.f / Rr; s.b = bb; s.kimp = kk * imp * bk;
+    }
+  }
+  __syncwarp(qm);  // completed contact slots visible to the quad
+  int n_ss = 0, css = 0;  // leg-leg contacts of this env: count and slot of the (last) one
   float knee_hits = 0.f, torso_hits = 0.f;
-  int own_list = 0, own_count = 0;  // contacts in which this lane's leg takes part (3 bits per entry)
+  int own_list = 0, own_count = 0;  // world-vs-leg contacts in which this lane's leg takes part (3 bits per entry)
   int part_all = 0;                 // participation code of this lane in every contact (4 bits per contact)
 #pragma unroll 1
   for (int c = 0; c < ncon; c++) {
     const ContactSlot &s = es.con[c];
-    any_ss |= (s.code1 >= 0 && s.code2 >= 0);
+    const bool is_ss = (s.code1 >= 0 && s.code2 >= 0);
+    if (is_ss) { n_ss++; css = c; }
     {
       const int pc = participation(s, k);
       part_all |= pc << (4 * c);
-      if (pc) { own_list |= c << (3 * own_count); own_count++; }
+      if (pc && !is_ss) { own_list |= c << (3 * own_count); own_count++; }
     }
     if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
     if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
 
+  // A leg-leg contact couples two legs, so its rows do not fit the arrow structure.  One such contact (the common
+  // rare case) is applied to the arrow solve as a rank-<=4 update (Woodbury, below); two or more go the dense way.
+  const bool one_ss = n_ss == 1, dense_env = n_ss >= 2;
   if (want_stale && k == 0) { es.st_hits[0] = knee_hits; es.st_hits[1] = torso_hits; }
   PHASE_SYNC();
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
@@ -1114,15 +1132,15 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     // has the cdofs), so the 4 lanes of a quad build different contacts at the same time; the trip count is the
     // warp-wide maximum of contacts per leg (typically 1-2), not the number of contacts of the env.
     __syncwarp(qm);
-    if (!__all_sync(qm, any_ss)) {
-      const int nown_w = __reduce_max_sync(qm, any_ss ? 0 : own_count);
+    if (!__all_sync(qm, dense_env)) {
+      const int nown_w = __reduce_max_sync(qm, dense_env ? 0 : own_count);
 #pragma unroll 1
       for (int i = 0; i < nown_w; i++) {
         const int c = (own_list >> (3 * i)) & 7;
         const ContactSlot &s = es.con[c];
         const float *wv = es.conW[c];
         const float W00 = wv[0];
-        if (i < own_count && !any_ss && W00 > 0.f) {
+        if (i < own_count && !dense_env && W00 > 0.f) {
           const float W01 = wv[1], W02 = wv[2], W11 = wv[3], W22 = wv[4];
           const V3 r = V3{s.r[0], s.r[1], s.r[2]};
           const int pc = (part_all >> (4 * c)) & 15;
@@ -1167,14 +1185,14 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   PHASE_SYNC();
   // Newton direction: search = -H^-1 grad
   float hb[6], hl[3];
-  if (__any_sync(qm, any_ss)) {  // rare: some env of this warp has a leg-leg contact (H still holds M + diagonal terms there)
+  if (__any_sync(qm, dense_env)) {  // very rare: some env of this warp has two or more leg-leg contacts (H holds M + diagonal terms there)
     DenseIO io;
     io.H = H;
 #pragma unroll
     for (int d = 0; d < 6; d++) { io.gb[d] = gb[d]; io.hb[d] = 0.f; }
 #pragma unroll
     for (int j = 0; j < 3; j++) { io.gl[j] = gl[j]; io.hl[j] = 0.f; io.cd[j] = cd[j]; io.ba[j] = ba[j]; io.bo[j] = bo[j]; }
-    dense_newton_direction(es, ncon, k, any_ss, qbase, io, rowJ);
+    dense_newton_direction(es, ncon, k, dense_env, qbase, io, rowJ);
 #pragma unroll
     for (int d = 0; d < 6; d++) hb[d] = io.hb[d];
 #pragma unroll
@@ -1184,7 +1202,86 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   {
     float tb[6], tl[3];
     tree_solve(H, gb, gl, tb, tl, qm);
-    if (!any_ss) {
+    if (__any_sync(qm, one_ss)) {
+      // Rare: one leg-leg contact.  With A the arrow matrix just factorised (M + diagonal rows + world-vs-leg contact
+      // blocks) and J, D the <=4 active pyramid-edge rows of that contact, (A + J^T D J) x = g is solved as
+      //   (D^-1 + J A^-1 J^T) y = J A^-1 g ,  x = A^-1 (g - J^T y).
+      // The rows have no base columns (the base moves both legs alike) and 3 entries on each of the two legs, held by
+      // those legs' lanes.  Quads without such a contact run along with zero rows (y = 0).
+      const ContactSlot &s = es.con[css];
+      const int pc = (part_all >> (4 * css)) & 15;
+      const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
+      const float sg = one_ss ? ((d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f)) : 0.f;
+      const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+      float cn[3], ct1[3], ct2[3];  // contact-frame components of this leg's columns
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const V3 col = cd[j].l + cross(cd[j].a, r);
+        const float w = (dep != 0 && j <= dep) ? sg : 0.f;
+        cn[j] = w * (s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z);
+        ct1[j] = w * (s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z);
+        ct2[j] = w * (s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z);
+      }
+      const float ja = rowJ[css * kBlock];
+      const float de = (one_ss && ja < 0.f) ? s.D : 0.f;  // weight of this lane's edge (0: inactive)
+      float je[4][3], S[4][4], t[4], dinv[4];
+      const float zb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float dd = __shfl_sync(qm, de, qbase + e);
+        const float on = dd > 0.f ? 1.f : 0.f;
+        dinv[e] = dd > 0.f ? 1.f / dd : 1.f;
+        const float em = ((e & 1) ? -s.mu : s.mu) * on;
+#pragma unroll
+        for (int j = 0; j < 3; j++) je[e][j] = fmaf(em, (e >> 1) ? ct2[j] : ct1[j], on * cn[j]);
+        t[e] = qsum(je[e][0] * tl[0] + je[e][1] * tl[1] + je[e][2] * tl[2], qm);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float ub[6], ul[3];
+        tree_solve(H, zb, je[e], ub, ul, qm);  // column e of A^-1 J^T
+#pragma unroll
+        for (int i = 0; i <= e; i++) S[e][i] = qsum(je[i][0] * ul[0] + je[i][1] * ul[1] + je[i][2] * ul[2], qm);
+        S[e][e] += dinv[e];
+      }
+      // 4x4 Cholesky of S (SPD: D^-1 > 0 on the diagonal, J A^-1 J^T >= 0) and the two triangular solves
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) {
+          float v = S[i][j];
+#pragma unroll
+          for (int q = 0; q < j; q++) v = fmaf(-S[i][q], S[j][q], v);
+          S[i][j] = (i == j) ? sqrtf(v) : v / S[j][j];
+        }
+      float y[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        float v = t[i];
+#pragma unroll
+        for (int q = 0; q < i; q++) v = fmaf(-S[i][q], y[q], v);
+        y[i] = v / S[i][i];
+      }
+#pragma unroll
+      for (int i = 3; i >= 0; i--) {
+        float v = y[i];
+#pragma unroll
+        for (int q = i + 1; q < 4; q++) v = fmaf(-S[q][i], y[q], v);
+        y[i] = v / S[i][i];
+      }
+      float g2[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) g2[j] = gl[j] - (y[0] * je[0][j] + y[1] * je[1][j] + y[2] * je[2][j] + y[3] * je[3][j]);
+      float xb2[6], xl2[3];
+      tree_solve(H, gb, g2, xb2, xl2, qm);
+      if (one_ss) {
+#pragma unroll
+        for (int d = 0; d < 6; d++) tb[d] = xb2[d];
+#pragma unroll
+        for (int j = 0; j < 3; j++) tl[j] = xl2[j];
+      }
+    }
+    if (!dense_env) {
 #pragma unroll
       for (int d = 0; d < 6; d++) hb[d] = tb[d];
 #pragma unroll

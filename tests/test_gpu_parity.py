@@ -201,7 +201,8 @@ def test_obstacle_contact_sets_single_substep():
 
 def test_leg_leg_contacts_take_the_dense_path():
     """Random joint configurations in the air: ~10 % of envs have penetrating leg-leg sphere pairs, which couple two
-    legs in the Hessian and exercise the dense fallback of the Newton direction."""
+    legs in the Hessian: one such contact is a low-rank (Woodbury) update of the arrow solve, two or more take the
+    dense fallback of the Newton direction.  Both groups are checked."""
     env = common.make_env(environment_timestep=0.004, **QUIET)
     n = 512
     h, O, O32 = _pair(env, n, debug=True)
@@ -222,6 +223,9 @@ def test_leg_leg_contacts_take_the_dense_path():
     act = (d["contact_dist"][:, :5] < 0) & (np.arange(5)[None] < d["ncon"][:, None])
     ss = (act & np.isin(d["contact_geom"][:, :5, 0], sph) & np.isin(d["contact_geom"][:, :5, 1], sph)).any(1)
     assert ss.sum() > 20
+    nss = (act & np.isin(d["contact_geom"][:, :5, 0], sph) & np.isin(d["contact_geom"][:, :5, 1], sph)).sum(1)
+    one, many = nss == 1, nss >= 2
+    assert one.sum() > 10 and many.sum() >= 3, (one.sum(), many.sum())
     cd, cg = h.rt.dbg["dbg_contact_dist"].cpu().numpy(), h.rt.dbg["dbg_contact_geom"].cpu().numpy()
     got, ref = _active_sets(cd, cg), _active_sets(d["contact_dist"], d["contact_geom"], d["ncon"])
     loose = _active_sets(d["contact_dist"], d["contact_geom"], d["ncon"], eps=1e-6)
@@ -233,6 +237,9 @@ def test_leg_leg_contacts_take_the_dense_path():
     assert np.median(e_c[ss]) <= 2.5 * np.median(e_32[ss]) + 1e-4
     assert np.quantile(e_c[ss], 0.9) <= 2.5 * np.quantile(e_32[ss], 0.9) + 1e-2
     assert np.median(e_c[~ss]) <= 2.5 * np.median(e_32[~ss]) + 1e-4
+    for grp in (one, many):  # low-rank path and dense path separately
+        assert np.median(e_c[grp]) <= 2.5 * np.median(e_32[grp]) + 1e-4
+        assert np.quantile(e_c[grp], 0.9) <= 2.5 * np.quantile(e_32[grp], 0.9) + 1e-2
 
 
 def test_episode_and_autoreset_fused():
