@@ -100,6 +100,8 @@ struct BlockShared {
   DerivedConsts d;
   EnvShared env[kEnvsPerBlock];
   float rows[3 * kMaxCon * kBlock];  // contact-edge row scalars: [buffer][contact][thread]
+  float4 lsq[kMaxCon * kBlock];      // line search, per contact-edge row: (Jaref, jv, qa, qb) ...
+  float lsc[kMaxCon * kBlock];       // ... and qc   ([contact][thread]; zero for slots past the env's contacts)
   float mat[45 * kBlock];            // per-lane copy of the mass matrix blocks: [element][thread]
 };
 
@@ -417,7 +419,8 @@ __device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
 // memory at out[(n*kMaxCon + c)*kBlock].
 template <int N>
 __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int k, const S6 cd[3], const V3 ba[3], const V3 bo[3],
-                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int ncon_w, int part_all, float *out) {
+                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int qbase, int ncon_w,
+                                             int part_all, bool ss_w, float *out) {
   S6 W1[N];  // spatial velocity of this leg's link2 (depth 1) under v_n; link3 adds vl[2]*cd[2]
 #pragma unroll
   for (int n = 0; n < N; n++) {
@@ -432,23 +435,32 @@ __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int 
     const V3 r = V3{s.r[0], s.r[1], s.r[2]};
     const int pc = (part_all >> (4 * c)) & 15;  // 0 for c >= ncon
     const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
-    const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
     V3 pv[N];
 #pragma unroll
     for (int n = 0; n < N; n++) {
       S6 W = fma6(dep == 2 ? vl[n][2] : 0.f, cd[2], W1[n]);
-      V3 t = W.l + cross(W.a, r);
-      pv[n] = dep ? V3{sg * t.x, sg * t.y, sg * t.z} : V3{0.f, 0.f, 0.f};
+      pv[n] = W.l + cross(W.a, r);  // velocity of the contact point as carried by this leg's touching link
     }
+    float rs;  // sign of the row (folded into the result: the row is linear in pv)
+    if (ss_w) {  // some env of the warp has a leg-leg contact: two legs may contribute, sum over the quad
+      const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
 #pragma unroll
-    for (int n = 0; n < N; n++) pv[n] = qsum3(pv[n], qm);
+      for (int n = 0; n < N; n++) pv[n] = qsum3(V3{sg * pv[n].x, sg * pv[n].y, sg * pv[n].z}, qm);
+      rs = 1.f;
+    } else {  // world-vs-leg contacts only: exactly one leg touches, take its value
+      const int c1 = s.code1, c2 = s.code2;
+      const int src = qbase + ((((c2 >= 0) ? c2 : c1) >> 2) & 3);
+      rs = c < ncon ? (c2 >= 0 ? 1.f : -1.f) : 0.f;
+#pragma unroll
+      for (int n = 0; n < N; n++) pv[n] = V3{__shfl_sync(qm, pv[n].x, src), __shfl_sync(qm, pv[n].y, src), __shfl_sync(qm, pv[n].z, src)};
+    }
     const float t0 = et2 ? s.frame[6] : s.frame[3], t1 = et2 ? s.frame[7] : s.frame[4], t2 = et2 ? s.frame[8] : s.frame[5];
     const float em = esgn * s.mu;
 #pragma unroll
     for (int n = 0; n < N; n++) {
       float jn = s.frame[0] * pv[n].x + s.frame[1] * pv[n].y + s.frame[2] * pv[n].z;
       float jt = t0 * pv[n].x + t1 * pv[n].y + t2 * pv[n].z;
-      out[(n * kMaxCon + c) * kBlock] = fmaf(em, jt, jn);
+      out[(n * kMaxCon + c) * kBlock] = rs * fmaf(em, jt, jn);
     }
   }
 }
@@ -957,6 +969,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   // A leg-leg contact couples two legs, so its rows do not fit the arrow structure.  One such contact (the common
   // rare case) is applied to the arrow solve as a rank-<=4 update (Woodbury, below); two or more go the dense way.
   const bool one_ss = n_ss == 1, dense_env = n_ss >= 2;
+  const bool ss_w = __any_sync(qm, n_ss > 0);
   if (want_stale && k == 0) { es.st_hits[0] = knee_hits; es.st_hits[1] = torso_hits; }
   PHASE_SYNC();
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
@@ -1004,7 +1017,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int d = 0; d < 6; d++) { v3b[0][d] = L.vb[d]; v3b[1][d] = L.wb[d]; v3b[2][d] = sb[d]; }
 #pragma unroll
     for (int j = 0; j < 3; j++) { v3l[0][j] = L.vl[j]; v3l[1][j] = L.wl[j]; v3l[2][j] = sl[j]; }
-    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, ncon_w, part_all, rowA);
+    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, qbase, ncon_w, part_all, ss_w, rowA);
   }
   float cost_w, cost_s, gauss_w;
   float jaw_f[3], jaw_l[3], jas_f[3], jas_l[3];
@@ -1305,7 +1318,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       for (int d = 0; d < 6; d++) v1b[0][d] = hb[d];
 #pragma unroll
       for (int j = 0; j < 3; j++) v1l[0][j] = hl[j];
-      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, ncon_w, part_all, rowA);  // jv of the contact-edge rows
+      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, qbase, ncon_w, part_all, ss_w, rowA);  // jv of the contact-edge rows
     }
     float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];
     float q1l = 0.f, q2l = 0.f;
@@ -1318,6 +1331,17 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
     for (int d = 0; d < 6; d++) { sn = fmaf(hb[d], hb[d], sn); q1l = fmaf(hb[d], Mab[d] - fs_b[d], q1l); q2l = fmaf(hb[d], mvb[d], q2l); }
     const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
+    // quadratic coefficients of the contact-edge rows, once per line search (one 16-byte + one 4-byte load per row and
+    // stage instead of three loads, three selects and six multiplies)
+    float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
+    float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < kMaxCon; c++) {
+      const bool con = c < ncon;
+      const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
+      lsq[c * kBlock] = make_float4(ja, jv, 0.5f * ja * ja * D, jv * ja * D);
+      lsc[c * kBlock] = 0.5f * jv * jv * D;
+    }
     const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
 
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
@@ -1355,9 +1379,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
 #pragma unroll
       for (int c = 0; c < kMaxCon; c++) {  // unrolled and select-guarded: no loop or divergence branches
-        const bool con = c < ncon;
-        const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
-        const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
+        const float4 q4 = lsq[c * kBlock];
+        const float ja = q4.x, jv = q4.y, qa = q4.z, qb = q4.w, qc = lsc[c * kBlock];
 #pragma unroll
         for (int p = 0; p < 3; p++) {
           const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
