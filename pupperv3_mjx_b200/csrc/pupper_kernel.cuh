@@ -29,6 +29,13 @@ namespace pupper {
 #ifndef PUPPER_PHASE_SYNC
 #define PUPPER_PHASE_SYNC 0
 #endif
+// A/B switches of individual optimisations (tools/jobs/ab.sh builds the variants and times them on one box)
+#ifndef PUPPER_ROWS_BCAST
+#define PUPPER_ROWS_BCAST 0  // single-source shuffle instead of the quad butterfly in contact_rows: fewer instructions, yet 1.5-2.3 % SLOWER (A/B on one B200)
+#endif
+#ifndef PUPPER_LS_HOIST
+#define PUPPER_LS_HOIST 1
+#endif
 // Experiment switch: CTA barriers at phase boundaries to keep a CTA's warps in step so they share
 // instruction-cache fills (`no_instruction` is a top stall reason, profiles/r1_summary.md).  Measured
 // A/B on B200: no difference at 4096 or 65,536 envs, so it is off.
@@ -442,7 +449,7 @@ __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int 
       pv[n] = W.l + cross(W.a, r);  // velocity of the contact point as carried by this leg's touching link
     }
     float rs;  // sign of the row (folded into the result: the row is linear in pv)
-    if (ss_w) {  // some env of the warp has a leg-leg contact: two legs may contribute, sum over the quad
+    if (ss_w || !PUPPER_ROWS_BCAST) {  // some env of the warp has a leg-leg contact: two legs may contribute, sum over the quad
       const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
 #pragma unroll
       for (int n = 0; n < N; n++) pv[n] = qsum3(V3{sg * pv[n].x, sg * pv[n].y, sg * pv[n].z}, qm);
@@ -1333,6 +1340,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
     // quadratic coefficients of the contact-edge rows, once per line search (one 16-byte + one 4-byte load per row and
     // stage instead of three loads, three selects and six multiplies)
+#if PUPPER_LS_HOIST
     float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
     float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
 #pragma unroll
@@ -1342,6 +1350,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       lsq[c * kBlock] = make_float4(ja, jv, 0.5f * ja * ja * D, jv * ja * D);
       lsc[c * kBlock] = 0.5f * jv * jv * D;
     }
+#endif
     const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
 
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
@@ -1379,8 +1388,14 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
 #pragma unroll
       for (int c = 0; c < kMaxCon; c++) {  // unrolled and select-guarded: no loop or divergence branches
+#if PUPPER_LS_HOIST
         const float4 q4 = lsq[c * kBlock];
         const float ja = q4.x, jv = q4.y, qa = q4.z, qb = q4.w, qc = lsc[c * kBlock];
+#else
+        const bool con = c < ncon;
+        const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
+        const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
+#endif
 #pragma unroll
         for (int p = 0; p < 3; p++) {
           const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;

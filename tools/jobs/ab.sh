@@ -1,0 +1,16 @@
+# ab.sh <envs-list> <variant names...>: times build/variants/<name>.so back to back on ONE box (3 rounds, interleaved)
+mkdir -p gpurun_out
+ENVS=$1; shift
+for round in 1 2 3; do
+  for v in "$@"; do
+    for n in $ENVS; do
+      PUPPER_ENV_LIB=$PWD/build/variants/$v.so python bench.py --steps 200 --warmup 5 --skip-cpu --envs $n > gpurun_out/ab_$v.json 2> gpurun_out/ab_$v.err || tail -3 gpurun_out/ab_$v.err
+      python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/ab_$v.json')); print('round $round %-12s %6d  %.4g  p50 %.4f' % ('$v', $n, d['value'], d['ms_per_step_quantiles']['p50']))
+except Exception as e: print('bench failed $v', e)
+PY
+    done
+  done
+done
