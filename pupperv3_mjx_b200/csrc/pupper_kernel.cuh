@@ -36,6 +36,12 @@ namespace pupper {
 #ifndef PUPPER_LS_HOIST
 #define PUPPER_LS_HOIST 1
 #endif
+#ifndef PUPPER_ZFOLD
+#define PUPPER_ZFOLD 1   // structural zeros folded by hand (the compiler may not drop 0*x terms)
+#endif
+#ifndef PUPPER_FR_HOIST
+#define PUPPER_FR_HOIST 1  // friction-row line-search coefficients hoisted out of the stage loop
+#endif
 // Experiment switch: CTA barriers at phase boundaries to keep a CTA's warps in step so they share
 // instruction-cache fills (`no_instruction` is a top stall reason, profiles/r1_summary.md).  Measured
 // A/B on B200: no difference at 4096 or 65,536 envs, so it is off.
@@ -107,6 +113,7 @@ struct BlockShared {
   DerivedConsts d;
   EnvShared env[kEnvsPerBlock];
   float rows[3 * kMaxCon * kBlock];  // contact-edge row scalars: [buffer][contact][thread]
+  float4 lsf[6 * kBlock];            // line search, per friction-loss row j: [2j] (Jaref, jv, R f, qc), [2j+1] linear-zone corrections
   float4 lsq[kMaxCon * kBlock];      // line search, per contact-edge row: (Jaref, jv, qa, qb) ...
   float lsc[kMaxCon * kBlock];       // ... and qc   ([contact][thread]; zero for slots past the env's contacts)
   float mat[45 * kBlock];            // per-lane copy of the mass matrix blocks: [element][thread]
@@ -178,16 +185,14 @@ __device__ __forceinline__ void tree_matvec_smem(const float *sm, const float xb
 
 // In-place leaves-first Cholesky.  On exit: D = L_k (3x3 lower), C = Y_k = L_k^-1 C_k,
 // B = chol(B + sum_k (Badd_k - Y_k^T Y_k)) (lower, replicated).  Badd may be null.
+// The DIAGONAL entries of D and B hold the reciprocals 1 / l_ii (the solves multiply instead of dividing).
 __device__ __forceinline__ void tree_factor(TreeMat &A, const float *Badd, unsigned qm) {
-  float l00 = sqrtf(A.D[0]);
-  float i00 = 1.f / l00;
+  float i00 = rsqrtf(A.D[0]);
   float l10 = A.D[1] * i00, l20 = A.D[3] * i00;
-  float l11 = sqrtf(A.D[2] - l10 * l10);
-  float i11 = 1.f / l11;
+  float i11 = rsqrtf(A.D[2] - l10 * l10);
   float l21 = (A.D[4] - l20 * l10) * i11;
-  float l22 = sqrtf(A.D[5] - l20 * l20 - l21 * l21);
-  float i22 = 1.f / l22;
-  A.D[0] = l00; A.D[1] = l10; A.D[2] = l11; A.D[3] = l20; A.D[4] = l21; A.D[5] = l22;
+  float i22 = rsqrtf(A.D[5] - l20 * l20 - l21 * l21);
+  A.D[0] = i00; A.D[1] = l10; A.D[2] = i11; A.D[3] = l20; A.D[4] = l21; A.D[5] = i22;  // diagonals hold 1 / l_ii
 #pragma unroll
   for (int d = 0; d < 6; d++) {
     float y0 = A.C[0][d] * i00;
@@ -212,15 +217,15 @@ __device__ __forceinline__ void tree_factor(TreeMat &A, const float *Badd, unsig
       float s = A.B[tri(i, j)];
 #pragma unroll
       for (int p = 0; p < j; p++) s = fmaf(-A.B[tri(i, p)], A.B[tri(j, p)], s);
-      A.B[tri(i, j)] = (i == j) ? sqrtf(s) : s / A.B[tri(j, j)];
+      A.B[tri(i, j)] = (i == j) ? rsqrtf(s) : s * A.B[tri(j, j)];  // diagonals hold 1 / l_ii
     }
 }
 
-// x = A^-1 g with the factor produced by tree_factor
+// x = A^-1 g with the factor produced by tree_factor (reciprocal diagonals)
 __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], const float gl[3], float xb[6], float xl[3], unsigned qm) {
-  float z0 = gl[0] / F.D[0];
-  float z1 = (gl[1] - F.D[1] * z0) / F.D[2];
-  float z2 = (gl[2] - F.D[3] * z0 - F.D[4] * z1) / F.D[5];
+  float z0 = gl[0] * F.D[0];
+  float z1 = (gl[1] - F.D[1] * z0) * F.D[2];
+  float z2 = (gl[2] - F.D[3] * z0 - F.D[4] * z1) * F.D[5];
   float y[6];
 #pragma unroll
   for (int d = 0; d < 6; d++) {
@@ -232,14 +237,14 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
     float s = y[i];
 #pragma unroll
     for (int p = 0; p < i; p++) s = fmaf(-F.B[tri(i, p)], y[p], s);
-    y[i] = s / F.B[tri(i, i)];
+    y[i] = s * F.B[tri(i, i)];
   }
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
     float s = y[i];
 #pragma unroll
     for (int p = i + 1; p < 6; p++) s = fmaf(-F.B[tri(p, i)], xb[p], s);
-    xb[i] = s / F.B[tri(i, i)];
+    xb[i] = s * F.B[tri(i, i)];
   }
   float w0 = z0, w1 = z1, w2 = z2;
 #pragma unroll
@@ -248,9 +253,9 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
     w1 = fmaf(-F.C[1][d], xb[d], w1);
     w2 = fmaf(-F.C[2][d], xb[d], w2);
   }
-  xl[2] = w2 / F.D[5];
-  xl[1] = (w1 - F.D[4] * xl[2]) / F.D[2];
-  xl[0] = (w0 - F.D[1] * xl[1] - F.D[3] * xl[2]) / F.D[0];
+  xl[2] = w2 * F.D[5];
+  xl[1] = (w1 - F.D[4] * xl[2]) * F.D[2];
+  xl[0] = (w0 - F.D[1] * xl[1] - F.D[3] * xl[2]) * F.D[0];
 }
 
 __device__ __noinline__ float impedance_curve_generic(float x, float mid, float power) {
@@ -598,10 +603,15 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       const int b = b0 + j;
       pos[j] = pp + rotate(V3{m.body_pos[b][0], m.body_pos[b][1], m.body_pos[b][2]}, pq);
       Q4 q = qmul(pq, Q4{m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
-      axis[j] = rotate(V3{0.f, 0.f, 1.f}, q);
       float sn, cs;
       sincos_small(L.ql[j] * 0.5f, &sn, &cs);
+#if PUPPER_ZFOLD
+      axis[j] = rotate_z(q);
+      rot[j] = qmul_zrot(q, cs, sn);
+#else
+      axis[j] = rotate(V3{0.f, 0.f, 1.f}, q);
       rot[j] = qmul(q, Q4{cs, 0.f, 0.f, sn});
+#endif
       xip[j] = pos[j] + rotate(V3{m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]}, rot[j]);
       M3 Ri = qmat(qmul(rot[j], Q4{m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]}));
       const float *di = &es.inertia[(b - 1) * 3];
@@ -732,9 +742,14 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
     for (int j = 2; j >= 0; j--) {
       S6 f = inert_mul(ci[j], ca[j]) + motion_cross_force(cv[j], inert_mul(ci[j], cv[j]));
+#if PUPPER_ZFOLD
+      cf = (j == 2) ? f : cf + f;
+      crb = (j == 2) ? ci[j] : crb + ci[j];
+#else
       cf = cf + f;
-      bias_l[j] = dot6(cd[j], cf);
       crb = crb + ci[j];
+#endif
+      bias_l[j] = dot6(cd[j], cf);
       S6 F = inert_mul(crb, cd[j]);  // crb_cdof of dof j
 #pragma unroll
       for (int jj = 0; jj <= j; jj++) M.D[tri(j, jj)] = dot6(F, cd[jj]);
@@ -744,7 +759,11 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       for (int i = 0; i < 3; i++) M.C[j][3 + i] = dot(ba[i], F.a) + dot(bo[i], F.l);
     }
     // base: own body + the 4 leg subtrees
+#if PUPPER_ZFOLD
+    S6 fb = S6{cross(cib.h, cab.l), cib.m * cab.l} + motion_cross_force(cvb, inert_mul(cib, cvb));  // cab.a = 0
+#else
     S6 fb = inert_mul(cib, cab) + motion_cross_force(cvb, inert_mul(cib, cvb));
+#endif
     S6 cfb = fb + qsum6(cf, qm);
     Inertia crbb;
     crbb.xx = cib.xx + qsum(crb.xx, qm); crbb.yy = cib.yy + qsum(crb.yy, qm); crbb.zz = cib.zz + qsum(crb.zz, qm);
@@ -1340,6 +1359,19 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
     // quadratic coefficients of the contact-edge rows, once per line search (one 16-byte + one 4-byte load per row and
     // stage instead of three loads, three selects and six multiplies)
+#if PUPPER_FR_HOIST
+    float4 *lsf = const_cast<float4 *>(sh.lsf) + threadIdx.x;
+    float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;  // friction rows: quadratic-zone coefficients, common to all step sizes
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const float ja = fJ[j], jv = hl[j];
+      const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
+      const float lv = fl[j] * jv, hr = -0.5f * rff[j];
+      fb0 += qa; fb1 += qb; fb2 += qc;
+      lsf[(2 * j) * kBlock] = make_float4(ja, jv, rff[j], qc);
+      lsf[(2 * j + 1) * kBlock] = make_float4(fl[j] * (hr - ja) - qa, -lv - qb, fl[j] * (hr + ja) - qa, lv - qb);
+    }
+#endif
 #if PUPPER_LS_HOIST
     float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
     float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
@@ -1355,10 +1387,30 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
     auto eval3 = [&](const float a[3], LSPoint out[3]) {
+#if PUPPER_FR_HOIST
+      float s0[3] = {fb0, fb0, fb0}, s1[3] = {fb1, fb1, fb1}, s2[3] = {fb2, fb2, fb2};
+      const float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+#else
       float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
       float b0 = 0.f, b1 = 0.f, b2 = 0.f;  // friction rows: quadratic-zone coefficients, common to the three points
+#endif
 #pragma unroll
       for (int j = 0; j < 3; j++) {
+#if PUPPER_FR_HOIST
+        {
+          const float4 a4 = lsf[(2 * j) * kBlock], c4 = lsf[(2 * j + 1) * kBlock];
+          const float ja = a4.x, jv = a4.y, rf = a4.z, qc = a4.w;
+#pragma unroll
+          for (int p = 0; p < 3; p++) {
+            const float x = fmaf(a[p], jv, ja);
+            const bool neg = x <= -rf;
+            const float lin = (neg || (x >= rf)) ? 1.f : 0.f;  // branch-free: 0/1 weight of the correction
+            s0[p] = fmaf(lin, neg ? c4.x : c4.z, s0[p]);
+            s1[p] = fmaf(lin, neg ? c4.y : c4.w, s1[p]);
+            s2[p] = fmaf(-lin, qc, s2[p]);
+          }
+        }
+#else
         {
           const float ja = fJ[j], jv = hl[j];
           const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
@@ -1376,6 +1428,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             s2[p] = fmaf(-lin, qc, s2[p]);
           }
         }
+#endif
         if (lsign[j] != 0.f) {
           const float ja = lJ[j], jv = lsign[j] * hl[j];
           const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];

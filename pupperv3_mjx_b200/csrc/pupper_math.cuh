@@ -70,6 +70,14 @@ __device__ __forceinline__ V3 rotate(V3 v, Q4 q) {
   return V3{2.f * (uv * u.x) + k * v.x + 2.f * q.w * c.x, 2.f * (uv * u.y) + k * v.y + 2.f * q.w * c.y,
             2.f * (uv * u.z) + k * v.z + 2.f * q.w * c.z};
 }
+// rotate((0,0,1), q) and q * (cs,0,0,sn) with the structural zeros dropped (same values for finite inputs)
+__device__ __forceinline__ V3 rotate_z(Q4 q) {
+  const float k = q.w * q.w - (q.x * q.x + q.y * q.y + q.z * q.z);
+  return V3{2.f * (q.z * q.x) + 2.f * q.w * q.y, 2.f * (q.z * q.y) - 2.f * q.w * q.x, 2.f * (q.z * q.z) + k};
+}
+__device__ __forceinline__ Q4 qmul_zrot(Q4 a, float cs, float sn) {
+  return Q4{a.w * cs - a.z * sn, a.x * cs + a.y * sn, a.y * cs - a.x * sn, a.w * sn + a.z * cs};
+}
 struct M3 {  // row-major 3x3
   float m[9];
 };
