@@ -33,15 +33,10 @@ namespace pupper {
 #ifndef PUPPER_ROWS_BCAST
 #define PUPPER_ROWS_BCAST 0  // single-source shuffle instead of the quad butterfly in contact_rows: fewer instructions, yet 1.5-2.3 % SLOWER (A/B on one B200)
 #endif
-#ifndef PUPPER_LS_HOIST
-#define PUPPER_LS_HOIST 1
-#endif
 #ifndef PUPPER_ZFOLD
 #define PUPPER_ZFOLD 1   // structural zeros folded by hand (the compiler may not drop 0*x terms)
 #endif
-#ifndef PUPPER_FR_HOIST
-#define PUPPER_FR_HOIST 1  // friction-row line-search coefficients hoisted out of the stage loop
-#endif
+
 // Experiment switch: CTA barriers at phase boundaries to keep a CTA's warps in step so they share
 // instruction-cache fills (`no_instruction` is a top stall reason, profiles/r1_summary.md).  Measured
 // A/B on B200: no difference at 4096 or 65,536 envs, so it is off.
@@ -1357,46 +1352,59 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
     for (int d = 0; d < 6; d++) { sn = fmaf(hb[d], hb[d], sn); q1l = fmaf(hb[d], Mab[d] - fs_b[d], q1l); q2l = fmaf(hb[d], mvb[d], q2l); }
     const float gq0 = gauss, gq1 = q1l, gq2 = 0.5f * q2l;
-    // quadratic coefficients of the contact-edge rows, once per line search (one 16-byte + one 4-byte load per row and
-    // stage instead of three loads, three selects and six multiplies)
-#if PUPPER_FR_HOIST
+    // Quadratic models of this lane's rows, built once per line search and kept in lane-private shared memory (the
+    // stage loop then needs two 16-byte loads per friction row, one 16-byte + one 4-byte load per contact-edge row).
+    // The cost model at alpha = 0 (MJX's p0) falls out of the same pass: same sums, same order as eval3 below.
     float4 *lsf = const_cast<float4 *>(sh.lsf) + threadIdx.x;
+    float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
+    float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
     float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;  // friction rows: quadratic-zone coefficients, common to all step sizes
+    float fc[3][4];                         // friction rows: linear-zone corrections (kept for the alpha = 0 pass only)
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const float ja = fJ[j], jv = hl[j];
       const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
       const float lv = fl[j] * jv, hr = -0.5f * rff[j];
       fb0 += qa; fb1 += qb; fb2 += qc;
+      // linear zones replace (qa, qb, qc) by (f(-R f/2 -+ ja), -+f jv, 0): the difference is added where they apply
+      fc[j][0] = fl[j] * (hr - ja) - qa; fc[j][1] = -lv - qb; fc[j][2] = fl[j] * (hr + ja) - qa; fc[j][3] = lv - qb;
       lsf[(2 * j) * kBlock] = make_float4(ja, jv, rff[j], qc);
-      lsf[(2 * j + 1) * kBlock] = make_float4(fl[j] * (hr - ja) - qa, -lv - qb, fl[j] * (hr + ja) - qa, lv - qb);
+      lsf[(2 * j + 1) * kBlock] = make_float4(fc[j][0], fc[j][1], fc[j][2], fc[j][3]);
     }
-#endif
-#if PUPPER_LS_HOIST
-    float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
-    float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
+    float z0 = fb0, z1 = fb1, z2 = fb2;  // sums at alpha = 0
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      {
+        const float x = fJ[j];
+        const bool neg = x <= -rff[j];
+        const float lin = (neg || (x >= rff[j])) ? 1.f : 0.f;
+        z0 = fmaf(lin, neg ? fc[j][0] : fc[j][2], z0);
+        z1 = fmaf(lin, neg ? fc[j][1] : fc[j][3], z1);
+        z2 = fmaf(-lin, 0.5f * hl[j] * hl[j] * fD[j], z2);
+      }
+      if (lsign[j] != 0.f) {
+        const float ja = lJ[j], jv = lsign[j] * hl[j];
+        const float on = ja < 0.f ? 1.f : 0.f;
+        z0 = fmaf(on, 0.5f * ja * ja * lD[j], z0); z1 = fmaf(on, jv * ja * lD[j], z1); z2 = fmaf(on, 0.5f * jv * jv * lD[j], z2);
+      }
+    }
 #pragma unroll
     for (int c = 0; c < kMaxCon; c++) {
       const bool con = c < ncon;
       const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
-      lsq[c * kBlock] = make_float4(ja, jv, 0.5f * ja * ja * D, jv * ja * D);
-      lsc[c * kBlock] = 0.5f * jv * jv * D;
+      const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
+      lsq[c * kBlock] = make_float4(ja, jv, qa, qb);
+      lsc[c * kBlock] = qc;
+      const float on = ja < 0.f ? 1.f : 0.f;
+      z0 = fmaf(on, qa, z0); z1 = fmaf(on, qb, z1); z2 = fmaf(on, qc, z2);
     }
-#endif
     const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
 
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
     auto eval3 = [&](const float a[3], LSPoint out[3]) {
-#if PUPPER_FR_HOIST
       float s0[3] = {fb0, fb0, fb0}, s1[3] = {fb1, fb1, fb1}, s2[3] = {fb2, fb2, fb2};
-      const float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-#else
-      float s0[3] = {0.f, 0.f, 0.f}, s1[3] = {0.f, 0.f, 0.f}, s2[3] = {0.f, 0.f, 0.f};
-      float b0 = 0.f, b1 = 0.f, b2 = 0.f;  // friction rows: quadratic-zone coefficients, common to the three points
-#endif
 #pragma unroll
       for (int j = 0; j < 3; j++) {
-#if PUPPER_FR_HOIST
         {
           const float4 a4 = lsf[(2 * j) * kBlock], c4 = lsf[(2 * j + 1) * kBlock];
           const float ja = a4.x, jv = a4.y, rf = a4.z, qc = a4.w;
@@ -1410,25 +1418,6 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             s2[p] = fmaf(-lin, qc, s2[p]);
           }
         }
-#else
-        {
-          const float ja = fJ[j], jv = hl[j];
-          const float qa = 0.5f * ja * ja * fD[j], qb = jv * ja * fD[j], qc = 0.5f * jv * jv * fD[j];
-          const float lv = fl[j] * jv, hr = -0.5f * rff[j];
-          // linear zones replace (qa, qb, qc) by (f(-R f/2 -+ ja), -+f jv, 0): add the difference where they apply
-          const float dn0 = fl[j] * (hr - ja) - qa, dn1 = -lv - qb, dp0 = fl[j] * (hr + ja) - qa, dp1 = lv - qb;
-          b0 += qa; b1 += qb; b2 += qc;
-#pragma unroll
-          for (int p = 0; p < 3; p++) {
-            const float x = fmaf(a[p], jv, ja);
-            const bool neg = x <= -rff[j];
-            const float lin = (neg || (x >= rff[j])) ? 1.f : 0.f;  // branch-free: 0/1 weight of the correction
-            s0[p] = fmaf(lin, neg ? dn0 : dp0, s0[p]);
-            s1[p] = fmaf(lin, neg ? dn1 : dp1, s1[p]);
-            s2[p] = fmaf(-lin, qc, s2[p]);
-          }
-        }
-#endif
         if (lsign[j] != 0.f) {
           const float ja = lJ[j], jv = lsign[j] * hl[j];
           const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
@@ -1440,15 +1429,9 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         }
       }
 #pragma unroll
-      for (int c = 0; c < kMaxCon; c++) {  // unrolled and select-guarded: no loop or divergence branches
-#if PUPPER_LS_HOIST
+      for (int c = 0; c < kMaxCon; c++) {  // unrolled, zero coefficients past the env's contacts: no loop or divergence branches
         const float4 q4 = lsq[c * kBlock];
         const float ja = q4.x, jv = q4.y, qa = q4.z, qb = q4.w, qc = lsc[c * kBlock];
-#else
-        const bool con = c < ncon;
-        const float ja = con ? rowJ[c * kBlock] : 0.f, jv = con ? rowA[c * kBlock] : 0.f, D = con ? es.con[c].D : 0.f;
-        const float qa = 0.5f * ja * ja * D, qb = jv * ja * D, qc = 0.5f * jv * jv * D;
-#endif
 #pragma unroll
         for (int p = 0; p < 3; p++) {
           const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
@@ -1457,21 +1440,25 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
 #pragma unroll
       for (int p = 0; p < 3; p++) {
-        float t0 = gq0 + qsum(s0[p] + b0, qm), t1 = gq1 + qsum(s1[p] + b1, qm), t2 = gq2 + qsum(s2[p] + b2, qm);
+        float t0 = gq0 + qsum(s0[p], qm), t1 = gq1 + qsum(s1[p], qm), t2 = gq2 + qsum(s2[p], qm);
         out[p].alpha = a[p];
         out[p].cost = a[p] * a[p] * t2 + a[p] * t1 + t0;
         out[p].d0 = 2.f * a[p] * t2 + t1;
         out[p].d1 = 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f);
       }
     };
-    LSPoint p0 = LSPoint{0.f, 0.f, 0.f, 1.f}, lo = p0, hi = p0;
+    LSPoint p0, lo, hi;
+    {
+      const float t0 = gq0 + qsum(z0, qm), t1 = gq1 + qsum(z1, qm), t2 = gq2 + qsum(z2, qm);
+      p0 = LSPoint{0.f, t0, t1, 2.f * t2 + (t2 == 0.f ? kMinVal : 0.f)};
+    }
+    lo = p0; hi = p0;
     bool swap = true, ls_on = true;
-    const int nstage = 2 + m.ls_iterations;
+    const int nstage = 1 + m.ls_iterations;  // stage 0: the Newton point of p0; stages 1..: bracket refinements
 #pragma unroll 1
     for (int stage = 0; stage < nstage; stage++) {
       float a3[3];
-      if (stage == 0) { a3[0] = a3[1] = a3[2] = 0.f; }
-      else if (stage == 1) { a3[0] = a3[1] = a3[2] = p0.alpha - p0.d0 / p0.d1; }
+      if (stage == 0) { a3[0] = a3[1] = a3[2] = p0.alpha - p0.d0 / p0.d1; }
       else {
         if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) ls_on = false;
         if (!__any_sync(qm, ls_on)) break;  // warp-uniform exit; finished envs idle through the remaining stages
@@ -1479,8 +1466,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
       LSPoint pt[3];
       eval3(a3, pt);
-      if (stage == 0) { p0 = pt[0]; }
-      else if (stage == 1) {
+      if (stage == 0) {
         lo = pt[0];
         if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
       } else if (ls_on) {
