@@ -821,40 +821,52 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     ccode1[2] = ccode2[2] = cs1[2] = cs2[2] = -1; ctype[2] = 1; cpos[2] = cn[2] = V3{0.f, 0.f, 0.f};
     ccode1[3] = ccode2[3] = cs1[3] = cs2[3] = -1; ctype[3] = 2; cpos[3] = cn[3] = V3{0.f, 0.f, 0.f};
     const int maxp = m.max_geom_pairs;
-    // sphere-box: broad phase keeps the max_geom_pairs pairs with the smallest bounding-sphere
-    // distance over all 8*nbox pairs (pair index = sphere*nbox + box); lane i runs narrow phase i.
+    // sphere-box: broad phase keeps the max_geom_pairs pairs with the smallest bounding-sphere distance over all
+    // 8*nbox pairs (pair index = sphere*nbox + box, ties to the lower index); the pair of rank i gets narrow phase on
+    // lane i.  One pass per lane keeps its own 4 best pairs sorted, a 4-round merge over the quad ranks them, and the
+    // 4 narrow phases then run side by side.
     if (m.nbox > 0) {
       const int nbox = m.nbox;
-      uint32_t taken0 = 0u, taken1 = 0u;  // per own sphere, bit per box
-      for (int r = 0; r < maxp && r < 8 * nbox; r++) {
-        float bk = kInf;
-        int bi = 0x7fffffff;
-        for (int i = 0; i < 2; i++) {
-          uint32_t taken = i ? taken1 : taken0;
-          for (int bx = 0; bx < nbox; bx++) {
-            if ((taken >> bx) & 1u) continue;
-            V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sc[i];
-            float key = sqrtf(dot(d, d)) - (m.sphere_radius[2 * k + i] + sh.d.box_rbound[bx]);
-            int id = (2 * k + i) * nbox + bx;
-            if (key < bk || (key == bk && id < bi)) { bk = key; bi = id; }
-          }
+      float k0 = kInf, k1 = kInf, k2 = kInf, k3 = kInf;
+      int i0 = 0x7fffffff, i1 = 0x7fffffff, i2 = 0x7fffffff, i3 = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const float rs = m.sphere_radius[2 * k + i];
+#pragma unroll 1
+        for (int bx = 0; bx < nbox; bx++) {
+          V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sc[i];
+          const float key = sqrtf(dot(d, d)) - (rs + sh.d.box_rbound[bx]);
+          const int id = (2 * k + i) * nbox + bx;  // ids grow along the pass, so strict '<' keeps ties in index order
+          const bool c0 = key < k0, c1 = key < k1, c2 = key < k2, c3 = key < k3;
+          k3 = c2 ? k2 : (c3 ? key : k3); i3 = c2 ? i2 : (c3 ? id : i3);
+          k2 = c1 ? k1 : (c2 ? key : k2); i2 = c1 ? i1 : (c2 ? id : i2);
+          k1 = c0 ? k0 : (c1 ? key : k1); i1 = c0 ? i0 : (c1 ? id : i1);
+          k0 = c0 ? key : k0; i0 = c0 ? id : i0;
         }
+      }
+      const int nr = min(min(maxp, 4), 8 * nbox);
+      int mine = -1;
+#pragma unroll 1
+      for (int r = 0; r < nr; r++) {
+        float bk = k0;
+        int bi = i0;
 #pragma unroll
         for (int s = 1; s <= 2; s <<= 1) {
           float ok = __shfl_xor_sync(qm, bk, s);
           int oi = __shfl_xor_sync(qm, bi, s);
           if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
         }
-        int sph = bi / nbox, bx = bi - sph * nbox;
-        if ((sph >> 1) == k) { if (sph & 1) taken1 |= 1u << bx; else taken0 |= 1u << bx; }
-        if ((r & 3) == k && r < 4) {  // narrow phase of selected pair r on lane r
-          V3 c = V3{es.sph[sph][0], es.sph[sph][1], es.sph[sph][2]};
-          V3 pp, nn;
-          float d = sphere_box(c, m.sphere_radius[sph], m.box_pos[bx], m.box_mat[bx], m.box_size[bx], pp, nn);
-          cdist[2] = d < 0.f ? d : kInf;
-          cpos[2] = pp; cn[2] = nn;
-          ccode1[2] = (sph >> 1) * 4 + 1 + (sph & 1); ccode2[2] = -1; cs1[2] = sph; cs2[2] = -1; cbox = bx;
-        }
+        if (bi == i0) { k0 = k1; i0 = i1; k1 = k2; i1 = i2; k2 = k3; i2 = i3; k3 = kInf; i3 = 0x7fffffff; }  // this lane's head won: pop it
+        if (r == k) mine = bi;
+      }
+      if (mine >= 0) {  // narrow phase of the pair ranked k
+        const int sph = mine / nbox, bx = mine - sph * nbox;
+        V3 c = V3{es.sph[sph][0], es.sph[sph][1], es.sph[sph][2]};
+        V3 pp, nn;
+        float d = sphere_box(c, m.sphere_radius[sph], m.box_pos[bx], m.box_mat[bx], m.box_size[bx], pp, nn);
+        cdist[2] = d < 0.f ? d : kInf;
+        cpos[2] = pp; cn[2] = nn;
+        ccode1[2] = (sph >> 1) * 4 + 1 + (sph & 1); ccode2[2] = -1; cs1[2] = sph; cs2[2] = -1; cbox = bx;
       }
     }
     // sphere-sphere: 24 leg-leg pairs, 6 per lane in MJX pair order; nothing to do unless one penetrates
