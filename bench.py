@@ -172,6 +172,9 @@ def run_cuda(args):
         rt.step(acts[t % n_act])
     for t in range(max(args.warmup, 3)):
         rt.step(acts[t % n_act])
+    if world > 1:  # NCCL communicator set-up belongs to the warm-up, not to the first timed all-reduce
+        dist.all_reduce(totals)
+        totals.div_(world)
     barrier()
     launches0 = rt.launches
     sampler = ClockSampler(local)
@@ -204,8 +207,7 @@ def run_cuda(args):
     # ---- end to end through the public API with host buffers -----------------------------------------------
     state = env_state_e2e = None
     h_act = [a.cpu().pin_memory() for a in acts]
-    h_obs = torch.empty((n, H * abi.OBS_DIM), dtype=torch.float32).pin_memory()
-    h_rd = torch.empty((2, n), dtype=torch.float32).pin_memory()
+    h_out = torch.empty(n * (H * abi.OBS_DIM + 2), dtype=torch.float32).pin_memory()  # obs | reward | done, as the runtime packs them
     d_act = torch.empty((n, 12), dtype=torch.float32, device=dev)
     e2e_steps = max(10, min(args.steps, 200))
     barrier()
@@ -214,9 +216,7 @@ def run_cuda(args):
     for t in range(e2e_steps):
         d_act.copy_(h_act[t % n_act], non_blocking=True)
         rt.step(d_act)
-        h_obs.copy_(rt.obs, non_blocking=True)
-        h_rd[0].copy_(rt.reward, non_blocking=True)
-        h_rd[1].copy_(rt.done, non_blocking=True)
+        h_out.copy_(rt.packed_outputs(), non_blocking=True)  # obs + reward + done in one device-to-host copy
         torch.cuda.current_stream().synchronize()  # the policy needs obs on the host before the next action
     e1.record()
     barrier()

@@ -140,9 +140,13 @@ class EnvRuntime:
         # env-major outputs; `guard_rows` extra rows (tests fill them with a sentinel to catch out-of-range writes)
         self.guard_rows = int(guard_rows)
         g = self.guard_rows
-        self._obs_full = torch.zeros((self.n_envs + g, H * abi.OBS_DIM), dtype=torch.float32, device=self.device)
-        self._reward_full = torch.zeros(self.n_envs + g, dtype=torch.float32, device=self.device)
-        self._done_full = torch.zeros(self.n_envs + g, dtype=torch.float32, device=self.device)
+        # obs | reward | done live back to back in one allocation, so a host-side consumer can fetch a step's results
+        # with a single device-to-host copy (`packed_outputs`)
+        nrow = self.n_envs + g
+        self._out_pack = torch.zeros(nrow * (H * abi.OBS_DIM + 2), dtype=torch.float32, device=self.device)
+        self._obs_full = self._out_pack[: nrow * H * abi.OBS_DIM].view(nrow, H * abi.OBS_DIM)
+        self._reward_full = self._out_pack[nrow * H * abi.OBS_DIM: nrow * (H * abi.OBS_DIM + 1)]
+        self._done_full = self._out_pack[nrow * (H * abi.OBS_DIM + 1):]
         self._metrics_full = torch.zeros((self.n_envs + g, abi.NMETRIC), dtype=torch.float32, device=self.device)
         self.obs, self.reward = self._obs_full[: self.n_envs], self._reward_full[: self.n_envs]
         self.done, self.metrics = self._done_full[: self.n_envs], self._metrics_full[: self.n_envs]
@@ -245,6 +249,16 @@ class EnvRuntime:
         self.launches += 1
 
     # ---- views -------------------------------------------------------------------------------------------------
+    def packed_outputs(self) -> torch.Tensor:
+        """Flat float32 view ``[obs (n*H*36) | reward (n) | done (n)]`` of the step outputs: one contiguous buffer, so
+        one copy moves a step's results to the host.  Split with ``split_packed``."""
+        return self._out_pack
+
+    def split_packed(self, flat: torch.Tensor):
+        """(obs [rows, H*36], reward [rows], done [rows]) views of a buffer laid out like ``packed_outputs``."""
+        rows, w = self.n_envs + self.guard_rows, self.cfg.observation_history * abi.OBS_DIM
+        return flat[: rows * w].view(rows, w), flat[rows * w: rows * (w + 1)], flat[rows * (w + 1):]
+
     def field(self, name: str) -> torch.Tensor:
         """SoA field ``[rows, n_envs]`` (a view without the stride padding)."""
         return self._fields[name][:, : self.n_envs]
