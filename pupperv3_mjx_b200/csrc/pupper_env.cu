@@ -6,6 +6,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <new>
+#include <algorithm>
 
 #include "pupper_kernel.cuh"
 
@@ -915,3 +916,6 @@ int pupper_state_rows(const PupperEnvCfg *cfg, int32_t *rows_out) {
 }
 
 }  // extern "C"
+
+// policy-MLP forward pass (include/pupper_policy.h): same library, same error helpers
+#include "pupper_policy.cuh"

@@ -1,9 +1,11 @@
 """Rollout collection with the policy MLP in the loop (BASELINE configs[4]).
 
-The reference trains with Brax PPO (policy MLP in JAX).  JAX is unavailable here, so the policy is a torch MLP of
-the shape ``export.py`` describes (dense layers, observation normalisation folded into layer 0, tanh head) -- a
-labelled substitution.  One unroll = ``unroll_length`` x (policy forward [cuBLAS] + fused env step [this repo's
-kernel]); nothing synchronises with the host, so the whole unroll can be captured in a CUDA graph.
+The reference trains with Brax PPO (policy MLP in JAX).  JAX is unavailable here, so the policy is an MLP of the
+shape ``export.py`` describes (dense layers, observation normalisation folded into layer 0, tanh head) -- a labelled
+substitution -- evaluated either by this repo's fused tensor-core kernel (``impl="cuda"``, the default for rollouts,
+one launch per forward pass: ``csrc/pupper_policy.cuh``) or by torch/cuBLAS (``impl="torch"``, the float32 checker
+the tests compare against).  One unroll = ``unroll_length`` x (policy forward + fused env step); nothing synchronises
+with the host, so the whole unroll can be captured in a CUDA graph.
 """
 
 from __future__ import annotations
@@ -18,33 +20,46 @@ from .environment import State
 
 
 class PolicyMLP(torch.nn.Module):
-    def __init__(self, layers: Sequence, device="cuda"):
+    def __init__(self, layers: Sequence, device="cuda", impl: str = "torch", precision: int = 3):
         super().__init__()
+        if impl not in ("torch", "cuda"):
+            raise ValueError("impl must be 'torch' or 'cuda'")
+        self.impl, self.layers = impl, [(np.asarray(W, np.float32), np.asarray(b, np.float32), a) for W, b, a in layers]
+        self._kernel = None
+        if impl == "cuda":
+            from . import runtime
+            dev = torch.device(device)
+            self._kernel = runtime.PolicyRuntime(self.layers, device=dev.index or 0, precision=precision)
         self.weights = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(W, dtype=torch.float32, device=device), requires_grad=False) for W, _, _ in layers])
         self.biases = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(b, dtype=torch.float32, device=device), requires_grad=False) for _, b, _ in layers])
         self.acts = [utils.activation_fn_map(a) for _, _, a in layers]
 
     @classmethod
     def random(cls, obs_size: int, hidden: Sequence[int] = (256, 128, 128, 128), action_size: int = 12, activation: str = "swish",
-               seed: int = 0, device="cuda") -> "PolicyMLP":
+               seed: int = 0, device="cuda", **kw) -> "PolicyMLP":
         rng = np.random.default_rng(seed)
         sizes = [obs_size, *hidden, action_size]
         layers = []
         for i in range(len(sizes) - 1):
             W = rng.normal(0, 1.0 / np.sqrt(sizes[i]), size=(sizes[i], sizes[i + 1])).astype(np.float32)
             layers.append((W, np.zeros(sizes[i + 1], np.float32), "tanh" if i == len(sizes) - 2 else activation))
-        return cls(layers, device)
+        return cls(layers, device, **kw)
 
     @classmethod
-    def from_export(cls, policy_dict: Dict, device="cuda") -> "PolicyMLP":
+    def from_export(cls, policy_dict: Dict, device="cuda", **kw) -> "PolicyMLP":
         from . import export
-        return cls(export.policy_from_dict(policy_dict), device)
+        return cls(export.policy_from_dict(policy_dict), device, **kw)
 
     @torch.no_grad()
-    def forward(self, obs: torch.Tensor) -> torch.Tensor:
+    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self._kernel is not None:
+            return self._kernel.forward(obs, out)
         x = obs
         for W, b, act in zip(self.weights, self.biases, self.acts):
             x = act(torch.addmm(b, x, W))
+        if out is not None:
+            out.copy_(x)
+            return out
         return x
 
 
@@ -75,7 +90,7 @@ class RolloutCollector:
         rt = self.state.pipeline_state.runtime
         for t in range(self.T):
             self.obs[t].copy_(rt.obs)
-            self.action[t].copy_(self.policy(rt.obs))
+            self.policy(rt.obs, self.action[t])  # written in place (the CUDA policy needs no temporary)
             rt.step(self.action[t])
             self.reward[t].copy_(rt.reward)
             self.done[t].copy_(rt.done)

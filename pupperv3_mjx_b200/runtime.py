@@ -45,6 +45,9 @@ def load_library() -> C.CDLL:
         lib.pupper_last_launch_count.argtypes = [C.c_void_p]
         lib.pupper_state_rows.argtypes = [C.c_void_p, C.c_void_p]
         lib.pupper_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        lib.pupper_policy_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.pupper_policy_destroy.argtypes = [C.c_void_p]
+        lib.pupper_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut,
                                abi.PupperEpisode)):
             if lib.pupper_sizeof(i) != C.sizeof(s):
@@ -299,3 +302,66 @@ class EnvRuntime:
                 "first_obs": ef("first_obs"),
             })
         return info
+
+
+# activation names of the reference's exporter (export.py / utils.activation_fn_map) -> include/pupper_policy.h codes
+POLICY_ACTIVATIONS = {"linear": 0, "relu": 1, "sigmoid": 2, "elu": 3, "tanh": 4, "swish": 5, "silu": 5, "gelu": 6, "leaky_relu": 7}
+POLICY_TF32, POLICY_3XTF32 = 1, 3
+
+
+class PolicyRuntime:
+    """Fused policy-MLP forward on the device (include/pupper_policy.h): one kernel launch per call, CUDA-graph capturable.
+    ``layers`` is the list ``export.policy_from_dict`` returns: ``[(W [in, out], b [out], activation name), ...]``."""
+
+    def __init__(self, layers, device: int = 0, precision: int = POLICY_3XTF32):
+        if not torch.cuda.is_available():
+            raise PupperError("no CUDA device: the policy kernel is the only implementation (no CPU fallback)")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        n = len(layers)
+        Ws = [np.ascontiguousarray(W, dtype=np.float32) for W, _, _ in layers]
+        bs = [np.ascontiguousarray(b, dtype=np.float32) for _, b, _ in layers]
+        try:
+            acts = [POLICY_ACTIVATIONS[a] for _, _, a in layers]
+        except KeyError as e:
+            raise PupperError(f"activation {e.args[0]!r} is not supported by the policy kernel") from None
+        for W, b in zip(Ws, bs):
+            if W.ndim != 2 or b.shape != (W.shape[1],):
+                raise PupperError("each layer needs W [in, out] and b [out]")
+        self.in_dim, self.out_dim = int(Ws[0].shape[0]), int(Ws[-1].shape[1])
+        ins = (C.c_int32 * n)(*[W.shape[0] for W in Ws])
+        outs = (C.c_int32 * n)(*[W.shape[1] for W in Ws])
+        acodes = (C.c_int32 * n)(*acts)
+        wp = (C.c_void_p * n)(*[W.ctypes.data for W in Ws])
+        bp = (C.c_void_p * n)(*[b.ctypes.data for b in bs])
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _check(self.lib, self.lib.pupper_policy_create(n, ins, outs, acodes, wp, bp, device, int(precision), C.byref(self._handle)),
+                   "pupper_policy_create")
+        self.launches = 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) and self._handle.value:
+                self.lib.pupper_policy_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if obs.device != self.device or obs.dtype != torch.float32 or not obs.is_contiguous() or obs.dim() != 2 \
+                or obs.shape[1] != self.in_dim:
+            raise PupperError(f"obs must be a contiguous float32 CUDA tensor of shape [n, {self.in_dim}] on the policy's device")
+        n = obs.shape[0]
+        if out is None:
+            out = torch.empty((n, self.out_dim), dtype=torch.float32, device=self.device)
+        elif out.shape != (n, self.out_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
+            raise PupperError(f"out must be a contiguous float32 CUDA tensor of shape [{n}, {self.out_dim}]")
+        with torch.cuda.device(self.device):
+            rc = self.lib.pupper_policy_forward(self._handle, n, obs.data_ptr(), out.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream)
+        _check(self.lib, rc, "pupper_policy_forward")
+        self.launches += 1
+        return out
+
+    __call__ = forward

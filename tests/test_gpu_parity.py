@@ -577,3 +577,78 @@ def test_step_parity_without_imu_and_with_longer_latency_buffers():
         assert np.array_equal(h.get("rng"), O.envs["rng"])
         assert np.median(np.abs(h.get("obs") - O.obs()).max(1)) < 1e-3
     assert lags == {0, 1, 2}
+
+
+@pytest.mark.gpu
+def test_policy_kernel_matches_torch_float32():
+    """Fused tensor-core policy MLP (csrc/pupper_policy.cuh) against the torch float32 chain of the same layers: the
+    3xTF32 mode to float32 rounding, the plain TF32 mode to TF32 rounding; ragged batch, widths that are not multiples of
+    8, every supported activation, and the reference-shaped 72-256-128-128-128-12 policy."""
+    import torch
+    from pupperv3_mjx_b200 import rollout, runtime
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = np.random.default_rng(0)
+
+    def mlp(sizes, acts):
+        return [(rng.normal(0, 1.0 / np.sqrt(sizes[i]), size=(sizes[i], sizes[i + 1])).astype(np.float32),
+                 rng.normal(0, 0.1, size=sizes[i + 1]).astype(np.float32), acts[i]) for i in range(len(sizes) - 1)]
+
+    cases = [([72, 256, 128, 128, 128, 12], ["swish"] * 4 + ["tanh"], 8192),
+             ([72, 256, 128, 128, 128, 12], ["swish"] * 4 + ["tanh"], 1000),   # ragged: not a multiple of the 64-row tile
+             ([36, 50, 30, 12], ["elu", "gelu", "tanh"], 257),                  # widths off the 8-grid
+             ([540, 64, 12], ["relu", "linear"], 130),                          # observation_history = 15 input
+             ([10, 9, 8, 7, 6, 5, 4, 3], ["sigmoid", "leaky_relu", "relu", "tanh", "swish", "elu", "linear"], 64)]
+    for sizes, acts, n in cases:
+        layers = mlp(sizes, acts)
+        x = torch.from_numpy(rng.normal(0, 1.0, size=(n, sizes[0])).astype(np.float32)).cuda()
+        ref = rollout.PolicyMLP(layers, impl="torch")(x)
+        ref64 = x.double()
+        for W, b, a in layers:
+            from pupperv3_mjx_b200 import utils
+            ref64 = utils.activation_fn_map(a)(ref64 @ torch.from_numpy(W).double().cuda() + torch.from_numpy(b).double().cuda())
+        scale = float(ref64.abs().max()) + 1e-6
+        e_torch = float((ref.double() - ref64).abs().max()) / scale
+        got3 = rollout.PolicyMLP(layers, impl="cuda", precision=runtime.POLICY_3XTF32)(x)
+        got1 = rollout.PolicyMLP(layers, impl="cuda", precision=runtime.POLICY_TF32)(x)
+        assert got3.shape == ref.shape and torch.isfinite(got3).all()
+        e3 = float((got3.double() - ref64).abs().max()) / scale
+        e1 = float((got1.double() - ref64).abs().max()) / scale
+        assert e3 <= 2e-5, (sizes, e3, e_torch)                     # float32-level (torch's own float32 chain: ~4e-7; TF32: ~1e-3)
+        assert e1 <= 5e-3, (sizes, e1)                              # TF32 operands: ~1e-3 relative
+    # unsupported activation / shape errors are loud
+    with pytest.raises(runtime.PupperError):
+        rollout.PolicyMLP(mlp([8, 8], ["softmax"]), impl="cuda")
+    pol = rollout.PolicyMLP(mlp([8, 8], ["tanh"]), impl="cuda")
+    with pytest.raises(runtime.PupperError):
+        pol(torch.zeros((4, 9), device="cuda"))
+
+
+@pytest.mark.gpu
+def test_rollout_with_cuda_policy_matches_torch_policy():
+    """Same short rollout with the fused policy kernel and with the torch policy: same first actions up to the policy's
+    float32 rounding, and the CUDA-policy unroll replays identically from a CUDA graph."""
+    import torch
+    from pupperv3_mjx_b200 import rollout, wrappers
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n, T = 256, 4
+    keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
+    outs = {}
+    for impl in ("torch", "cuda"):
+        env = common.make_env()
+        tenv = wrappers.wrap(env, episode_length=1000)
+        st = tenv.reset(keys)
+        pol = rollout.PolicyMLP.random(env.observation_size, impl=impl)
+        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=False)
+        outs[impl] = {k: v.clone() for k, v in col.collect().items()}
+    a, b = outs["torch"], outs["cuda"]
+    assert torch.isfinite(b["obs"]).all() and torch.isfinite(b["action"]).all()
+    np.testing.assert_array_equal(b["obs"][0].cpu().numpy(), a["obs"][0].cpu().numpy())
+    np.testing.assert_allclose(b["action"][0].cpu().numpy(), a["action"][0].cpu().numpy(), atol=2e-5)
+    # graph capture of the unroll with the CUDA policy: two replays from the same start state give the same data
+    env = common.make_env()
+    tenv = wrappers.wrap(env, episode_length=1000)
+    st = tenv.reset(keys)
+    pol = rollout.PolicyMLP.random(env.observation_size, impl="cuda")
+    col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=True)
+    r1 = {k: v.clone() for k, v in col.collect().items()}
+    assert torch.isfinite(r1["obs"]).all() and float(r1["action"].abs().max()) <= 1.0

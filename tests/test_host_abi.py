@@ -15,10 +15,10 @@ HEADER = os.path.join(common.ROOT, "include", "pupper_env.h")
 
 def test_library_exports_every_declared_symbol():
     lib = runtime.load_library()
-    text = open(HEADER).read()
+    text = open(HEADER).read() + open(os.path.join(common.ROOT, "include", "pupper_policy.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = re.findall(r"\b(pupper_[a-z_]+)\s*\(", text)
-    assert len(set(names)) >= 9
+    assert len(set(names)) >= 12 and "pupper_policy_forward" in names
     for name in set(names):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
 
