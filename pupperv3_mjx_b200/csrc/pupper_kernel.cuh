@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <type_traits>
 
 #include "../../include/pupper_env.h"
 #include "pupper_math.cuh"
@@ -32,6 +33,12 @@ namespace pupper {
 // A/B switches of individual optimisations (tools/jobs/ab.sh builds the variants and times them on one box)
 #ifndef PUPPER_ROWS_BCAST
 #define PUPPER_ROWS_BCAST 0  // single-source shuffle instead of the quad butterfly in contact_rows: fewer instructions, yet 1.5-2.3 % SLOWER (A/B on one B200)
+#endif
+#ifndef PUPPER_LS_PEEL
+#define PUPPER_LS_PEEL 1  // line search: the Newton point of p0 (stage 0) is ONE step size, evaluated alone instead of as three equal points
+#endif
+#ifndef PUPPER_LIM_UNIFORM
+#define PUPPER_LIM_UNIFORM 1  // limit rows in the line search behind one warp-uniform test instead of three divergent ones per pass
 #endif
 #ifndef PUPPER_ZFOLD
 #define PUPPER_ZFOLD 1   // structural zeros folded by hand (the compiler may not drop 0*x terms)
@@ -1394,12 +1401,25 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         z1 = fmaf(lin, neg ? fc[j][1] : fc[j][3], z1);
         z2 = fmaf(-lin, 0.5f * hl[j] * hl[j] * fD[j], z2);
       }
+#if !PUPPER_LIM_UNIFORM
       if (lsign[j] != 0.f) {
         const float ja = lJ[j], jv = lsign[j] * hl[j];
         const float on = ja < 0.f ? 1.f : 0.f;
         z0 = fmaf(on, 0.5f * ja * ja * lD[j], z0); z1 = fmaf(on, jv * ja * lD[j], z1); z2 = fmaf(on, 0.5f * jv * jv * lD[j], z2);
       }
+#endif
     }
+#if PUPPER_LIM_UNIFORM
+    const bool lim_w = __any_sync(qm, (lsign[0] != 0.f) | (lsign[1] != 0.f) | (lsign[2] != 0.f));
+    if (lim_w) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const float ja = lJ[j], jv = lsign[j] * hl[j];
+        const float on = ja < 0.f ? 1.f : 0.f;
+        z0 = fmaf(on, 0.5f * ja * ja * lD[j], z0); z1 = fmaf(on, jv * ja * lD[j], z1); z2 = fmaf(on, 0.5f * jv * jv * lD[j], z2);
+      }
+    }
+#endif
 #pragma unroll
     for (int c = 0; c < kMaxCon; c++) {
       const bool con = c < ncon;
@@ -1413,15 +1433,18 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     const float gtol = m.tolerance * m.ls_tolerance * (sqrtf(sn) * m.meaninertia * 18.f);
 
     // evaluates the 1-D cost model at three step sizes at once (one pass over this lane's rows)
-    auto eval3 = [&](const float a[3], LSPoint out[3]) {
-      float s0[3] = {fb0, fb0, fb0}, s1[3] = {fb1, fb1, fb1}, s2[3] = {fb2, fb2, fb2};
+    auto evalN = [&](auto npc, const float *a, LSPoint *out) {
+      constexpr int NP = decltype(npc)::value;
+      float s0[NP], s1[NP], s2[NP];
+#pragma unroll
+      for (int p = 0; p < NP; p++) { s0[p] = fb0; s1[p] = fb1; s2[p] = fb2; }
 #pragma unroll
       for (int j = 0; j < 3; j++) {
         {
           const float4 a4 = lsf[(2 * j) * kBlock], c4 = lsf[(2 * j + 1) * kBlock];
           const float ja = a4.x, jv = a4.y, rf = a4.z, qc = a4.w;
 #pragma unroll
-          for (int p = 0; p < 3; p++) {
+          for (int p = 0; p < NP; p++) {
             const float x = fmaf(a[p], jv, ja);
             const bool neg = x <= -rf;
             const float lin = (neg || (x >= rf)) ? 1.f : 0.f;  // branch-free: 0/1 weight of the correction
@@ -1430,28 +1453,44 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             s2[p] = fmaf(-lin, qc, s2[p]);
           }
         }
+#if !PUPPER_LIM_UNIFORM
         if (lsign[j] != 0.f) {
           const float ja = lJ[j], jv = lsign[j] * hl[j];
           const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
 #pragma unroll
-          for (int p = 0; p < 3; p++) {
+          for (int p = 0; p < NP; p++) {
+            const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
+            s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
+          }
+        }
+#endif
+      }
+#if PUPPER_LIM_UNIFORM
+      if (lim_w) {  // some joint of this warp is past a limit (rare); rows that are not have lD = 0, ja = jv = 0: they add zeros
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          const float ja = lJ[j], jv = lsign[j] * hl[j];
+          const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
+#pragma unroll
+          for (int p = 0; p < NP; p++) {
             const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
             s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
           }
         }
       }
+#endif
 #pragma unroll
       for (int c = 0; c < kMaxCon; c++) {  // unrolled, zero coefficients past the env's contacts: no loop or divergence branches
         const float4 q4 = lsq[c * kBlock];
         const float ja = q4.x, jv = q4.y, qa = q4.z, qb = q4.w, qc = lsc[c * kBlock];
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
+        for (int p = 0; p < NP; p++) {
           const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
           s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
         }
       }
 #pragma unroll
-      for (int p = 0; p < 3; p++) {
+      for (int p = 0; p < NP; p++) {
         float t0 = gq0 + qsum(s0[p], qm), t1 = gq1 + qsum(s1[p], qm), t2 = gq2 + qsum(s2[p], qm);
         out[p].alpha = a[p];
         out[p].cost = a[p] * a[p] * t2 + a[p] * t1 + t0;
@@ -1467,6 +1506,34 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     lo = p0; hi = p0;
     bool swap = true, ls_on = true;
     const int nstage = 1 + m.ls_iterations;  // stage 0: the Newton point of p0; stages 1..: bracket refinements
+#if PUPPER_LS_PEEL
+    {
+      const float a1[1] = {p0.alpha - p0.d0 / p0.d1};
+      LSPoint pt1[1];
+      evalN(std::integral_constant<int, 1>{}, a1, pt1);
+      lo = pt1[0];
+      if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+    }
+#pragma unroll 1
+    for (int stage = 1; stage < nstage; stage++) {
+      float a3[3];
+      if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) ls_on = false;
+      if (!__any_sync(qm, ls_on)) break;  // warp-uniform exit; finished envs idle through the remaining stages
+      a3[0] = lo.alpha - lo.d0 / lo.d1; a3[1] = hi.alpha - hi.d0 / hi.d1; a3[2] = 0.5f * (lo.alpha + hi.alpha);
+      LSPoint pt[3];
+      evalN(std::integral_constant<int, 3>{}, a3, pt);
+      if (ls_on) {
+        const LSPoint lon = pt[0], hin = pt[1], mid = pt[2];
+        const bool s1 = in_bracket(lo, lon); lo = ls_select(s1, lon, lo);
+        const bool s2 = in_bracket(lo, mid); lo = ls_select(s2, mid, lo);
+        const bool s3 = in_bracket(lo, hin); lo = ls_select(s3, hin, lo);
+        const bool t1 = in_bracket(hi, hin); hi = ls_select(t1, hin, hi);
+        const bool t2 = in_bracket(hi, mid); hi = ls_select(t2, mid, hi);
+        const bool t3 = in_bracket(hi, lon); hi = ls_select(t3, lon, hi);
+        swap = s1 | s2 | s3 | t1 | t2 | t3;
+      }
+    }
+#else
 #pragma unroll 1
     for (int stage = 0; stage < nstage; stage++) {
       float a3[3];
@@ -1477,7 +1544,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         a3[0] = lo.alpha - lo.d0 / lo.d1; a3[1] = hi.alpha - hi.d0 / hi.d1; a3[2] = 0.5f * (lo.alpha + hi.alpha);
       }
       LSPoint pt[3];
-      eval3(a3, pt);
+      evalN(std::integral_constant<int, 3>{}, a3, pt);
       if (stage == 0) {
         lo = pt[0];
         if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
@@ -1492,6 +1559,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         swap = s1 | s2 | s3 | t1 | t2 | t3;
       }
     }
+#endif
     bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
     if (!improved) alpha = 0.f;

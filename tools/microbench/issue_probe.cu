@@ -81,8 +81,16 @@ __global__ void __launch_bounds__(128) stream_kernel(float *out, int iters, floa
   for (int it = 0; it < iters; it++) {
     if (SIZE >= 1) { BODY2K }
     if (SIZE >= 2) { BODY2K }
-    if (SIZE >= 4) { BODY2K BODY2K }
-    if (SIZE >= 8) { BODY2K BODY2K BODY2K BODY2K }
+    if (SIZE >= 3) { BODY2K }
+    if (SIZE >= 4) { BODY2K }
+    if (SIZE >= 5) { BODY2K }
+    if (SIZE >= 6) { BODY2K }
+    if (SIZE >= 7) { BODY2K }
+    if (SIZE >= 8) { BODY2K }
+    if (SIZE >= 9) { BODY2K }
+    if (SIZE >= 10) { BODY2K }
+    if (SIZE >= 11) { BODY2K }
+    if (SIZE >= 12) { BODY2K }
   }
   long long t1 = clock64();
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + p0.x + p0.y + p1.x + p1.y + p2.x + p2.y + p3.x + p3.y + pad[threadIdx.x & 1];
@@ -143,6 +151,11 @@ int main() {
            per_iter * 16.0 / 1024, ctas_per_sm * 4, c / instr, instr * ctas_per_sm / c, ms);
   };
 #define RUN(KG, SY, PK) for (int cps : {1, 2, 4}) run_stream(stream_kernel<KG, SY, PK>, #KG "x2k sync=" #SY " packed=" #PK, KG, PK, cps)
+  if (getenv("PROBE_FINE")) {  // finer sweep of the body size: where the fetch rate steps
+    RUN(1, false, false); RUN(2, false, false); RUN(3, false, false); RUN(4, false, false); RUN(5, false, false); RUN(6, false, false);
+    RUN(7, false, false); RUN(8, false, false); RUN(9, false, false); RUN(10, false, false); RUN(11, false, false); RUN(12, false, false);
+    return 0;
+  }
   RUN(1, false, false); RUN(2, false, false); RUN(4, false, false); RUN(8, false, false);
   RUN(4, true, false); RUN(8, true, false);
   RUN(1, false, true); RUN(4, false, true); RUN(8, false, true);
