@@ -102,9 +102,29 @@ Executed FP32 work per env-step (source page, predicated-on thread instructions:
 
 Reading: issue-latency bound at 8 resident warps/SM (255 registers/thread, 0 spills in the hot path); DRAM traffic per
 launch stays below the algorithmic 2,044 B x envs (part of the state is still L2-resident), so there are no wasted
-re-reads and the HBM roofline fraction is <1 %; the FMA pipe is busy ~22 % at 65,536 envs. Stall mix: fixed-latency
-dependencies ("wait"), instruction fetch ("no_instruction": 17 k-instruction kernel, many branch targets),
-L1TEX ("long_scoreboard": prologue/epilogue global accesses), shared memory ("short_scoreboard").
+re-reads and the HBM roofline fraction is <3 %; the FMA pipe is busy ~28 % at 65,536 envs. Stall mix: instruction
+fetch ("no_instruction": a 16.5 k-instruction kernel whose substep loop body exceeds the 32 KB instruction-cache level,
+see the fetch ceiling below), fixed-latency dependencies ("wait"), shared memory ("short_scoreboard"),
+L1TEX ("long_scoreboard": prologue/epilogue global accesses).
+
+## The instruction-fetch ceiling (`tools/microbench/issue_probe.cu`, `PROBE_FINE=1`, same B200 pool)
+
+Straight-line FFMA code (8 independent chains, no memory traffic) looped over a body of the given size; cycles per
+instruction per warp / warp-instructions per clock per SMSP:
+
+| loop body | 1 warp/SMSP | 2 warps/SMSP | 4 warps/SMSP |
+|---|---|---|---|
+| 32 KB (2 k instr.) | 1.35 / 0.74 | 2.05 / 0.98 | 4.08 / 0.98 |
+| 64 - 128 KB | 3.15 - 3.22 / 0.31 | 2.93 - 3.01 / 0.67 - 0.68 | 7.3 - 8.0 / 0.50 - 0.55 |
+| 160 - 384 KB | 6.10 - 6.16 / 0.16 | 6.25 - 6.32 / 0.32 | 6.39 - 6.45 / 0.62 |
+
+The step kernel's substep loop is ~8.5 k SASS instructions (136 KB in address range, ~110 KB on the executed path), i.e.
+in the middle row: a warp that streams code from beyond the 32 KB level cannot issue faster than one instruction per
+~3 cycles, and an SMSP tops out at ~0.67 instructions/clock with two such warps.  The kernel runs at 4.04 cycles per
+instruction per warp (1.75 of them `no_instruction`) with one warp per SMSP at 4096 envs and at 0.49 instructions/clock
+per SMSP with two at 65,536 envs - 73 % of that ceiling.  More resident warps would need < 170 registers per thread
+(measured: spills cost more than the occupancy buys); the step that removes the ceiling is a kernel whose per-phase
+code is reused across several env groups while it is cache resident.
 
 ## Where the instructions and the stall samples go (65,536 envs; `tools/phase_hist.py`)
 
@@ -129,7 +149,12 @@ the state load/store and the lag-buffer / observation / reward / episode code.)
 | + packed participation codes, tabulated leg-leg pairs, cheaper friction-row accumulation | 1.71e7 | 4.94e7 |
 | + branch-free row accumulation in the line search | 1.86e7 | 5.42e7 |
 | + branch-free cost evaluation / force rows | 1.89e7 | 5.52e7 |
-| + branch-free bracket updates and contact selection, unrolled select-guarded contact rows (final) | 1.95e7 | 5.67e7 |
+| + branch-free bracket updates and contact selection, unrolled select-guarded contact rows | 1.95e7 | 5.67e7 |
+| + compact branch-free sincos, out-of-line generic impedance curve | 2.03e7 | - |
+| + a single leg-leg contact solved as a rank-4 Woodbury update of the arrow solve (no dense fallback in the tail steps) | 3.0e7 | 7.2e7 |
+| + contact slots completed by the quad in parallel, contact-edge quadratic coefficients hoisted out of the stage loop, reciprocal diagonals in the tree factor/solves, structural zeros folded, alpha = 0 model from the coefficient pass | 3.36e7 | 8.23e7 |
+| + line-search stage 0 evaluated as ONE step size (was three equal ones), limit rows behind one warp-uniform test (A/B on one box, 3 interleaved rounds, spread < 0.2 %) (final) | 3.43e7 | 8.31e7 |
+| `__builtin_expect` on the rare warp-uniform paths (block layout unchanged: ptxas keeps the cold blocks inline) | no change | no change |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
 | 256-thread CTAs | 1.48e7 | 4.48e7 |
