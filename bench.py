@@ -239,7 +239,7 @@ def run_cuda(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     bytes_per_launch = b_alg(H) * n
     achieved = bytes_per_launch / (ms * 1e-3) / 1e9
-    flop_per_step = 1.62e5  # executed FP32 flop per env-step of this kernel (ncu source page, profiles/r1_summary.md)
+    flop_per_step = 1.59e5  # executed FP32 flop per env-step of this kernel (ncu source page, profiles/r1_summary.md)
     traffic_4096 = 5.18e6  # dram__bytes_read+write per launch at 4096 envs from the ncu --set full capture (profiles/r1_summary.md)
     ffma_peak = runtime.measure_ffma_tflops(local)  # measured FP32 denominator (MEASURED_PEAKS.json has none)
     line = {
