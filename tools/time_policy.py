@@ -13,7 +13,7 @@ env = common.make_env()
 rand = functools.partial(dr.domain_randomize, rng=prng.split(prng.PRNGKey(2), n))
 tenv = wrappers.wrap(env, episode_length=1000, randomization_fn=rand)
 st = tenv.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), n)).view(np.int32)).to(dev))
-pol = rollout.PolicyMLP.random(env.observation_size)
+pol = rollout.PolicyMLP.random(env.observation_size, impl="torch")
 pol_c3 = rollout.PolicyMLP.random(env.observation_size, impl="cuda", precision=3)
 pol_c1 = rollout.PolicyMLP.random(env.observation_size, impl="cuda", precision=1)
 rt = st.pipeline_state.runtime
