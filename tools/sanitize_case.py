@@ -28,3 +28,16 @@ for debug in (False, True):
         h.step(common.actions(n, t))
     print("debug", debug, "finite", bool(np.isfinite(h.get("obs")).all()), "done", int(h.get("done").sum()))
 print("sanitize case finished")
+
+# fused policy kernel: ragged batch, widths off the 8-grid, every tiles-per-warp body, both precisions
+from pupperv3_mjx_b200 import rollout
+rng = np.random.default_rng(1)
+for sizes, nrow in (([72, 200, 96, 72, 64, 32, 12], 333), ([72, 256, 128, 128, 128, 12], 100), ([7, 5, 3], 1)):
+    layers = [(rng.normal(0, 0.2, size=(sizes[i], sizes[i + 1])).astype(np.float32), rng.normal(0, 0.1, size=sizes[i + 1]).astype(np.float32),
+               "tanh" if i == len(sizes) - 2 else "swish") for i in range(len(sizes) - 1)]
+    x = torch.randn((nrow, sizes[0]), device="cuda")
+    for prec in (1, 3):
+        y = rollout.PolicyMLP(layers, impl="cuda", precision=prec)(x)
+        torch.cuda.synchronize()
+        print("policy", sizes, nrow, prec, "finite", bool(torch.isfinite(y).all()))
+print("policy sanitize case finished")
