@@ -124,7 +124,8 @@ in the middle row: a warp that streams code from beyond the 32 KB level cannot i
 instruction per warp (1.75 of them `no_instruction`) with one warp per SMSP at 4096 envs and at 0.49 instructions/clock
 per SMSP with two at 65,536 envs - 73 % of that ceiling.  More resident warps would need < 170 registers per thread
 (measured: spills cost more than the occupancy buys); the step that removes the ceiling is a kernel whose per-phase
-code is reused across several env groups while it is cache resident (DESIGN.md section 6).
+code is reused across several env groups while it is cache resident, with the state handed between phases through shared
+memory so that the per-phase register working set allows 4 warps per SMSP (DESIGN.md section 6).
 
 ## Where the instructions and the stall samples go (65,536 envs; `tools/phase_hist.py`)
 
