@@ -245,8 +245,10 @@ def run_cuda(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: flat ground, {n} envs/GPU, {'no' if args.no_dr else 'full'} domain randomisation, H={H}, "
-                               f"fused episode/auto-reset, {'obstacle boxes, ' if args.obstacles else ''}5 substeps/step",
+        "config": {"workload": (f"configs[2]: obstacles.py box terrain (10 boxes, reference test/test_environment.py:28-41) with randomised pushes, "
+                                if args.obstacles else "configs[1]: flat ground, ") +
+                               f"{n} envs/GPU, {'no' if args.no_dr else 'full'} domain randomisation, H={H}, "
+                               f"fused episode/auto-reset, 5 substeps/step",
                    "envs_per_gpu": n, "settle_steps": args.settle, "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between timed steps (256 MB memset outside the event pairs)",
                    "timing": "mean of per-step CUDA event pairs on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -290,6 +292,27 @@ def run_cuda(args):
             extra[f"envs_{en}"] = {"value": en / (s0.elapsed_time(s1) / 50 * 1e-3), "unit": UNIT,
                                    "note": "flat ground, full DR, 50 back-to-back steps, state > L2 only at 65536"}
             del r2
+        # BASELINE configs[2]: obstacles.py box terrain with randomised pushes, 16384 envs
+        env_o = make_env(obstacles=True)
+        env_o.set_episode_params(1000, 1)
+        en = 16384
+        r2 = runtime.EnvRuntime(env_o.model_desc, env_o.env_cfg, en, device=local, episode=True)
+        sv, _ = dr.domain_randomize(env_o.sys, prng.split(prng.PRNGKey(2), en))
+        r2.set_dr(sv)
+        r2.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), en)).view(np.int32)).to(dev))
+        a2 = [(torch.rand((en, 12), generator=g, device=dev) - 0.5) for _ in range(4)]
+        for t in range(args.settle + 5):
+            r2.step(a2[t % 4])
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for t in range(50):
+            r2.step(a2[t % 4])
+        s1.record()
+        torch.cuda.synchronize()
+        extra["envs_16384_obstacles"] = {"value": en / (s0.elapsed_time(s1) / 50 * 1e-3), "unit": UNIT,
+                                         "note": "configs[2]: 10-box obstacles.py terrain, kicks on, full DR, 50 back-to-back steps"}
+        del r2
         # H = 15 at 65,536 envs: 380 MB of state + history per step, i.e. the one case that streams from HBM
         import common as _c
         env15 = _c.make_env(observation_history=15)

@@ -157,6 +157,7 @@ of the stall samples.)
 | + a single leg-leg contact solved as a rank-4 Woodbury update of the arrow solve (no dense fallback in the tail steps) | 3.0e7 | 7.2e7 |
 | + contact slots completed by the quad in parallel, contact-edge quadratic coefficients hoisted out of the stage loop, reciprocal diagonals in the tree factor/solves, structural zeros folded, alpha = 0 model from the coefficient pass | 3.36e7 | 8.23e7 |
 | + line-search stage 0 evaluated as ONE step size (was three equal ones), limit rows behind one warp-uniform test (A/B on one box, 3 interleaved rounds, spread < 0.2 %) (final) | 3.43e7 | 8.31e7 |
+| line-search contact rows skipped behind a warp-uniform test when no env of the warp has a 3rd / 4th / 5th contact (A/B, same box) | 3.42e7 / 3.43e7 / 3.44e7 (3.44e7 without) | 8.22e7 / 8.27e7 / 8.34e7 (8.34e7 without) |
 | `__builtin_expect` on the rare warp-uniform paths (block layout unchanged: ptxas keeps the cold blocks inline) | no change | no change |
 | `__launch_bounds__(128,3)` = 168 registers (1.0 KB spills) | 1.20e7 | 3.55e7 |
 | `__launch_bounds__(128,4)` = 128 registers (2.5 KB spills) | 9.8e6 | 2.51e7 |
