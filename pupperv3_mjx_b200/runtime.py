@@ -251,6 +251,102 @@ class EnvRuntime:
         _check(self.lib, rc, "pupper_step")
         self.launches += 1
 
+    # ---- host-buffer path: action in pinned host memory -> step -> obs | reward | done in pinned host memory ----------
+    def _chunk_structs(self, chunks: int):
+        """Per-chunk copies of the ABI structs with every per-env pointer advanced to the chunk's first env (the C ABI
+        takes plain pointers and a count, so a contiguous env range is just an offset; ranges start on multiples of 32 envs,
+        which keeps the SoA rows 128-byte aligned)."""
+        key = int(chunks)
+        if getattr(self, "_chunk_cache", None) and self._chunk_cache[0] == key and self._chunk_cache[1] is self._dr_struct:
+            return self._chunk_cache[2]
+        n, H = self.n_envs, self.cfg.observation_history
+        # range size: a whole number of kernel waves (2 CTAs of 32 envs per SM) when the batch is that large, so cutting the
+        # batch does not add partially filled waves; otherwise a multiple of 32 envs
+        wave = torch.cuda.get_device_properties(self.device).multi_processor_count * 2 * 32
+        size = (n + chunks - 1) // chunks
+        size = (size + wave - 1) // wave * wave if size >= wave else (size + 31) // 32 * 32
+        out = []
+        for e0 in range(0, n, size):
+            cnt = min(size, n - e0)
+            st = abi.PupperState()
+            st.stride = self.stride
+            for name in abi.STATE_FIELDS:
+                setattr(st, name, getattr(self.state, name) + 4 * e0)
+            st.obs = self.state.obs + 4 * e0 * H * abi.OBS_DIM
+            so = abi.PupperStepOut()
+            so.reward, so.done = self.out.reward + 4 * e0, self.out.done + 4 * e0
+            so.metrics = self.out.metrics + 4 * e0 * abi.NMETRIC
+            dr = None
+            if self._dr_struct is not None:
+                dr = abi.PupperDR()
+                dr.stride = self._dr_struct.stride
+                for name in abi.DR_ROWS:
+                    setattr(dr, name, getattr(self._dr_struct, name) + 4 * e0)
+            ep = None
+            if self.episode is not None:
+                ep = abi.PupperEpisode()
+                ep.stride = self.episode.stride
+                for name in abi.EPISODE_ROWS:
+                    setattr(ep, name, getattr(self.episode, name) + 4 * e0)
+                ep.first_obs = self.episode.first_obs + 4 * e0 * H * abi.OBS_DIM
+                ep.totals = self.episode.totals
+            out.append((e0, cnt, st, so, dr, ep, torch.cuda.Event(), torch.cuda.Event()))
+        self._chunk_cache = (key, self._dr_struct, out)
+        return out
+
+    def step_host(self, h_action: torch.Tensor, h_out: torch.Tensor, chunks: Optional[int] = None) -> torch.cuda.Event:
+        """One env step with HOST buffers: ``h_action`` [n, 12] float32 (pinned) in, ``h_out`` = ``obs | reward | done``
+        (the ``packed_outputs`` layout, pinned) out.  Returns the event to wait on before reading ``h_out``.
+
+        Large batches are cut into ``chunks`` contiguous env ranges that are pipelined over three streams (actions in,
+        step kernels in order, observations out), so the PCIe transfers of one range overlap the kernel of the next: at
+        65,536 envs the 19 MB of observations per step cost about as much as the step itself.  Small batches (the step
+        is latency bound and would not get shorter by splitting) take one chunk on the current stream."""
+        n, H = self.n_envs, self.cfg.observation_history
+        w = H * abi.OBS_DIM
+        if self.guard_rows or self.dbg:
+            raise PupperError("step_host is the production path: no guard rows, no debug taps")
+        if h_action.dtype != torch.float32 or h_action.numel() != n * abi.NU or h_out.dtype != torch.float32 or h_out.numel() != n * (w + 2):
+            raise PupperError("h_action must be float32 [n_envs, 12] and h_out float32 [n_envs * (H*36 + 2)]")
+        if chunks is None:
+            chunks = max(1, min(8, n // 16384))
+        if not hasattr(self, "_d_act"):
+            self._d_act = torch.empty((n, abi.NU), dtype=torch.float32, device=self.device)
+            self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
+            self._done_ev = torch.cuda.Event()
+        cur = torch.cuda.current_stream(self.device)
+        done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
+        if chunks <= 1:
+            self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
+            self.step(self._d_act)
+            h_out.copy_(self._out_pack, non_blocking=True)
+            done_ev.record(cur)
+            return done_ev
+        ha, flat = h_action.view(n, abi.NU), h_out.view(-1)
+        self._s_in.wait_stream(cur)
+        self._s_out.wait_stream(cur)
+        model = self._model
+        with torch.cuda.device(self.device):
+            for e0, cnt, st, so, dr, ep, ev_in, ev_k in self._chunk_structs(chunks):
+                with torch.cuda.stream(self._s_in):
+                    self._d_act[e0:e0 + cnt].copy_(ha[e0:e0 + cnt], non_blocking=True)
+                    ev_in.record(self._s_in)
+                cur.wait_event(ev_in)
+                rc = self.lib.pupper_step(model, cnt, C.byref(dr) if dr is not None else None, C.byref(st),
+                                          self._d_act.data_ptr() + 4 * e0 * abi.NU, C.byref(so),
+                                          C.byref(ep) if ep is not None else None, cur.cuda_stream)
+                _check(self.lib, rc, "pupper_step")
+                self.launches += 1
+                ev_k.record(cur)
+                with torch.cuda.stream(self._s_out):
+                    self._s_out.wait_event(ev_k)
+                    flat[e0 * w:(e0 + cnt) * w].copy_(self._out_pack[e0 * w:(e0 + cnt) * w], non_blocking=True)
+            with torch.cuda.stream(self._s_out):  # reward | done are adjacent: one copy after the last range
+                flat[n * w:].copy_(self._out_pack[n * w:], non_blocking=True)
+                done_ev.record(self._s_out)
+        cur.wait_event(done_ev)  # later work on the caller's stream sees a finished step
+        return done_ev
+
     # ---- views -------------------------------------------------------------------------------------------------
     def packed_outputs(self) -> torch.Tensor:
         """Flat float32 view ``[obs (n*H*36) | reward (n) | done (n)]`` of the step outputs: one contiguous buffer, so

@@ -653,3 +653,45 @@ def test_rollout_with_cuda_policy_matches_torch_policy():
     col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=True)
     r1 = {k: v.clone() for k, v in col.collect().items()}
     assert torch.isfinite(r1["obs"]).all() and float(r1["action"].abs().max()) <= 1.0
+
+
+@pytest.mark.gpu
+def test_step_host_chunked_pipeline_matches_plain_step():
+    """EnvRuntime.step_host (pinned host action in, obs|reward|done out; env ranges pipelined over three streams) leaves
+    exactly the state and outputs of the plain device-buffer step: ragged batch, DR, fused episode accounting, 1-5 chunks."""
+    import torch
+    from pupperv3_mjx_b200 import abi, domain_randomization as dr, prng, runtime
+    n = 333
+    env = common.make_env()
+    env.set_episode_params(5, 1)  # short episodes: auto-resets happen inside the test
+    sys_v, _ = dr.domain_randomize(env.sys, prng.split(prng.PRNGKey(2), n))
+    keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
+    w = env.env_cfg.observation_history * abi.OBS_DIM
+
+    def fresh():
+        rt = runtime.EnvRuntime(env.model_desc, env.env_cfg, n, episode=True)
+        rt.set_dr(sys_v)
+        rt.reset(keys)
+        return rt
+
+    ref = fresh()
+    ref_out = []
+    for t in range(12):
+        ref.step(torch.from_numpy(common.actions(n, t)).cuda())
+        ref_out.append(ref.packed_outputs().clone())
+    torch.cuda.synchronize()
+    for chunks in (1, 2, 3, 5):
+        rt = fresh()
+        h_out = torch.empty(n * (w + 2), dtype=torch.float32).pin_memory()
+        for t in range(12):
+            h_act = torch.from_numpy(common.actions(n, t)).pin_memory()
+            rt.step_host(h_act, h_out, chunks=chunks).synchronize()
+            np.testing.assert_array_equal(h_out.numpy(), ref_out[t].cpu().numpy(), err_msg=f"chunks={chunks} step={t}")
+        torch.cuda.synchronize()
+        for name in abi.STATE_FIELDS:
+            assert torch.equal(rt.field(name), ref.field(name)), (chunks, name)
+        for name in ("sum_reward", "length", "steps", "episode_done", "sum_metrics"):
+            assert torch.equal(rt.episode_field(name), ref.episode_field(name)), (chunks, name)
+        np.testing.assert_allclose(rt.episode_field("totals").cpu().numpy(), ref.episode_field("totals").cpu().numpy(), rtol=1e-5)
+    with pytest.raises(runtime.PupperError):
+        rt.step_host(torch.zeros((n, 11)).pin_memory(), h_out)
