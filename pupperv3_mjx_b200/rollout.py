@@ -70,10 +70,16 @@ class RolloutCollector:
     def __init__(self, tenv, policy: PolicyMLP, state: State, unroll_length: int, use_cuda_graph: bool = True):
         self.tenv, self.policy, self.state, self.T = tenv, policy, state, int(unroll_length)
         B, dev = state.obs.shape[0], state.obs.device
-        self.obs = torch.empty((self.T, B, state.obs.shape[1]), device=dev)
+        rt = state.pipeline_state.runtime
+        # The runtime keeps obs | reward | done of the last step back to back (packed_outputs), so ONE copy per step files
+        # all three: slot 0 holds the state the unroll starts from, slot t + 1 what step t produced.  obs[t] (the policy
+        # input of step t) is slot t, reward[t] / done[t] are slot t + 1.
+        self._slots = torch.empty((self.T + 1, rt.packed_outputs().numel()), device=dev)
+        w, rows = state.obs.shape[1], rt.n_envs + rt.guard_rows  # layout of packed_outputs: obs[rows, w] | reward[rows] | done[rows]
+        self.obs = self._slots[: self.T, : rows * w].unflatten(1, (rows, w))[:, :B]
+        self.reward = self._slots[1:, rows * w: rows * w + B]
+        self.done = self._slots[1:, rows * (w + 1): rows * (w + 1) + B]
         self.action = torch.empty((self.T, B, 12), device=dev)
-        self.reward = torch.empty((self.T, B), device=dev)
-        self.done = torch.empty((self.T, B), device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         if use_cuda_graph:
             self._unroll()  # warm-up (allocator, cuBLAS handles) outside the capture
@@ -89,12 +95,11 @@ class RolloutCollector:
 
     def _unroll(self):
         rt = self.state.pipeline_state.runtime
+        self._slots[0].copy_(rt.packed_outputs())
         for t in range(self.T):
-            self.obs[t].copy_(rt.obs)
             self.policy(rt.obs, self.action[t])  # written in place (the CUDA policy needs no temporary)
             rt.step(self.action[t])
-            self.reward[t].copy_(rt.reward)
-            self.done[t].copy_(rt.done)
+            self._slots[t + 1].copy_(rt.packed_outputs())
 
     def collect(self) -> Dict[str, torch.Tensor]:
         if self._graph is not None:
