@@ -110,7 +110,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = min(args.envs, 512)  # each step is a bounded sample of the workload's env batch
+    n = min(args.envs, 4096)  # each step is a bounded sample of the workload's env batch (the whole batch at the default size)
     env = make_env()
     env.set_episode_params(1000, 1)
     cores = host_cores()
