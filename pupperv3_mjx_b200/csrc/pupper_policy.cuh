@@ -282,10 +282,14 @@ __global__ void __launch_bounds__(32 * kPolWarps * NSPLIT) policy_kernel(const P
 
 }  // namespace pupper
 
+#include "pupper_policy_tc.cuh"
+
 struct PupperPolicy {
   pupper::PolicyParams params;  // device pointers filled in, n / obs / action set per call
   int device, precision, smem_bytes;
   std::vector<void *> allocs;
+  bool use_tc = false;          // TF32 mode on the tcgen05 kernel (every layer width <= 256)
+  pupper::TcParams tc;
 };
 
 extern "C" {
@@ -344,6 +348,42 @@ int pupper_policy_create(int n_layers, const int32_t *in_dims, const int32_t *ou
     if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "policy weight upload"); }
     P.layer[l] = pupper::PolicyLayer{reinterpret_cast<const float2 *>(dw), reinterpret_cast<const float *>(db), kp, np, N, activations[l]};
   }
+  // ---- tcgen05 path (TF32 mode, widths <= 256): weights packed per K-chunk as W^T in the K-major canonical UMMA layout ----
+  {
+    bool fits = precision == PUPPER_POLICY_TF32 && !getenv("PUPPER_POLICY_LEGACY");
+    for (int l = 0; l < n_layers && fits; l++) fits = in_dims[l] <= pupper::kTcMaxW && out_dims[l] <= pupper::kTcMaxW;
+    pupper::TcParams &T = pol->tc;
+    memset(&T, 0, sizeof(T));
+    int nchunk = 0;
+    for (int l = 0; l < n_layers && fits; l++) {
+      const int K = in_dims[l], N = out_dims[l], kp8 = (K + 7) / 8 * 8, np16 = (N + 15) / 16 * 16;
+      for (int n = 0; n < N; n++) T.bias[l][n] = biases[l][n];
+      T.layer[l] = pupper::TcLayer{kp8, np16, N, activations[l]};
+      const int kc_max = std::max(8, pupper::kTcBBytes / (np16 * 4) / 8 * 8);
+      for (int k0 = 0; k0 < kp8; k0 += kc_max) {
+        if (nchunk >= pupper::kTcMaxChunks) { fits = false; break; }
+        const int kc = std::min(kc_max, kp8 - k0);
+        std::vector<float> pack((size_t)np16 * kc, 0.f);
+        const int sbo = (kc / 4) * 32;  // floats between 8-row groups
+        for (int n = 0; n < N; n++)
+          for (int k = k0; k < std::min(K, k0 + kc); k++) {
+            const int kk = k - k0;
+            pack[(size_t)(n / 8) * sbo + (kk / 4) * 32 + (n % 8) * 4 + (kk % 4)] = weights[l][(size_t)k * N + n];
+          }
+        void *dw = nullptr;
+        e = cudaMalloc(&dw, pack.size() * sizeof(float));
+        if (e == cudaSuccess) { pol->allocs.push_back(dw); e = cudaMemcpy(dw, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice); }
+        if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "policy weight upload (tcgen05 layout)"); }
+        T.chunk[nchunk++] = pupper::TcChunk{reinterpret_cast<const float *>(dw), np16 * kc * 4, l, k0, kc, k0 + kc >= kp8 ? 1 : 0};
+      }
+    }
+    if (fits) {
+      T.n_chunks = nchunk; T.n_layers = n_layers; T.in_dim = in_dims[0];
+      e = cudaFuncSetAttribute(pupper::policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pupper::kTcSmemBytes);
+      if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "cudaFuncSetAttribute(policy_tc_kernel)"); }
+      pol->use_tc = true;
+    }
+  }
   e = cudaFuncSetAttribute(pupper::policy_kernel<1, PUPPER_POLICY_NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::policy_kernel<3, PUPPER_POLICY_NSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, pol->smem_bytes);
   if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "cudaFuncSetAttribute(policy_kernel)"); }
@@ -357,6 +397,14 @@ int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, f
   p.n = n; p.obs = obs; p.action = action;
   const int grid = (n + pupper::kPolRows - 1) / pupper::kPolRows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (policy->use_tc) {
+    pupper::TcParams t = policy->tc;
+    t.n = n; t.obs = obs; t.action = action;
+    pupper::policy_tc_kernel<<<(n + pupper::kTcRows - 1) / pupper::kTcRows, pupper::kTcThreads, pupper::kTcSmemBytes, s>>>(t);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "policy_tc_kernel launch");
+    return PUPPER_OK;
+  }
   constexpr int threads = 32 * pupper::kPolWarps * PUPPER_POLICY_NSPLIT;
   if (policy->precision == PUPPER_POLICY_TF32) pupper::policy_kernel<1, PUPPER_POLICY_NSPLIT><<<grid, threads, policy->smem_bytes, s>>>(p);
   else pupper::policy_kernel<3, PUPPER_POLICY_NSPLIT><<<grid, threads, policy->smem_bytes, s>>>(p);

@@ -1,0 +1,249 @@
+// pupper_policy_tc.cuh -- the policy MLP forward on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+// accumulators in tensor memory), used for PUPPER_POLICY_TF32 when every layer fits (widths <= 256).
+//
+// One CTA owns 128 rows (envs) and carries them through all layers:
+//   * A operand = the 128 x K activations of the current layer, resident in shared memory in the K-major canonical
+//     (no-swizzle) UMMA layout: element (r, k) at (r % 8) * 16 + (k / 4) * 128 + (r / 8) * 8192 bytes
+//     (8 rows x 16 bytes core matrices; leading-dimension byte offset 128, stride byte offset 8192 = a 256-wide row block);
+//   * B operand = the layer's weights as W^T [N, K], K-major, in the same canonical layout, packed on the host per
+//     K-chunk so that a chunk is one contiguous block of global memory (L2 resident) that ONE thread moves with a bulk
+//     async copy (cp.async.bulk, completion on an mbarrier) into one of three 32 KB buffers, two chunks ahead of the
+//     MMAs -- copies, MMAs and the epilogue overlap;
+//   * D = 128 lanes x N columns of float32 in tensor memory (256 columns allocated);
+//   * one thread issues the layer's K/8 tcgen05.mma instructions (M = 128, N = layer width padded to 16, K = 8 each) and
+//     commits them to an mbarrier; the 16 warps then read the accumulators back with tcgen05.ld (warp w: lane quadrant
+//     w % 4, every fourth 16-column group), add the bias, apply the activation and write the result straight into the A
+//     tile of the next layer (or to global memory after the last layer).
+// TF32 operands are the raw float32 bits (the tensor core reads the top 19), as in the mma.sync kernel's TF32 mode.
+#pragma once
+#include <vector>
+
+#include "../../include/pupper_policy.h"
+
+namespace pupper {
+
+constexpr int kTcRows = 128;             // rows per CTA = MMA M
+#ifndef PUPPER_TC_THREADS
+#define PUPPER_TC_THREADS 512
+#endif
+constexpr int kTcThreads = PUPPER_TC_THREADS;
+constexpr int kTcColSplit = kTcThreads / 128;  // warps per lane quadrant
+constexpr int kTcMaxW = 256;             // widest layer input / output
+constexpr int kTcABytes = kTcRows * kTcMaxW * 4;   // 128 KB activation tile
+constexpr int kTcBBytes = 32 * 1024;     // one weight chunk buffer
+constexpr int kTcBufs = 3;               // ... of three: copies run two chunks ahead
+constexpr int kTcSboA = (kTcMaxW / 4) * 128;       // bytes between 8-row groups of the A tile
+constexpr int kTcMaxChunks = 32;
+
+struct TcChunk {
+  const float *src;   // packed chunk in global memory
+  int bytes;          // np16 * kc * 4
+  int layer, k0, kc;  // K range [k0, k0 + kc) of the layer (multiples of 8)
+  int last;           // last chunk of its layer
+};
+struct TcLayer {
+  int kp8, np16, n_out, act;
+};
+struct TcParams {
+  TcChunk chunk[kTcMaxChunks];
+  TcLayer layer[PUPPER_POLICY_MAX_LAYERS];
+  float bias[PUPPER_POLICY_MAX_LAYERS][kTcMaxW];  // zero padded; kernel parameters live in the constant bank (uniform reads)
+  int n_chunks, n_layers, in_dim, n;
+  const float *obs;
+  float *action;
+};
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: start address, leading byte offset (between the two 16-byte K halves of one MMA), stride byte
+// offset (between 8-row groups); descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// kind::tf32, D = F32, A/B = TF32, both K-major, M = 128
+__device__ __forceinline__ uint32_t tc_instr_desc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcRows >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tTC_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra TC_DONE_%=;\n\tbra TC_WAIT_%=;\n\tTC_DONE_%=:\n\t}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// Epilogue of one layer for this warp: quadrant q (rows 32 q + lane), 16-column groups h, h + 2, ...
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue(const TcParams &p, const TcLayer &L, const float *bias, bool last, uint32_t tmem, unsigned char *smA,
+                                            int q, int h, int lane, int row0) {
+  const int r = 32 * q + lane;
+  unsigned char *arow = smA + (r & 7) * 16 + (r >> 3) * kTcSboA;
+  const int row = row0 + r;
+  for (int g = h; g < (L.np16 >> 4); g += kTcColSplit) {
+    float v[16];
+    tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * g), v);
+    const int c0 = 16 * g;
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = policy_act<ACT>(v[i] + bias[c0 + i]);
+    if (!last) {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        *reinterpret_cast<float4 *>(arow + ((c0 >> 2) + i) * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else if (row < p.n) {
+#pragma unroll
+      for (int i = 0; i < 16; i++)
+        if (c0 + i < L.n_out) p.action[(size_t)row * L.n_out + c0 + i] = v[i];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char *smA = tc_smem;
+  unsigned char *smB = tc_smem + kTcABytes;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tc_smem + kTcABytes + kTcBufs * kTcBBytes);  // full[3], empty[3], layer done
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcBufs + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcRows;
+  auto full_bar = [&](int b) { return tc_smem_u32(&bars[b]); };
+  auto empty_bar = [&](int b) { return tc_smem_u32(&bars[kTcBufs + b]); };
+  // One phase per layer, waited on by every thread in order.  (The buffers' "empty" barriers cannot serve here: a thread
+  // that skips their intermediate phases cannot tell phase k from phase k + 2 by parity.)
+  const uint32_t done_bar = tc_smem_u32(&bars[2 * kTcBufs]);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // weight chunk c -> buffer c % 3 as one bulk async copy; its bytes complete the buffer's "full" mbarrier
+  auto issue_chunk = [&](int c) {
+    const TcChunk &ch = p.chunk[c];
+    const uint32_t dst = tc_smem_u32(smB + (c % kTcBufs) * kTcBBytes), bar = full_bar(c % kTcBufs);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)ch.bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(ch.src),
+                 "r"((uint32_t)ch.bytes), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 32) {  // the copy thread
+    for (int b = 0; b < 2 * kTcBufs + 1; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[b])) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    issue_chunk(0);
+    if (p.n_chunks > 1) issue_chunk(1);
+  }
+  // layer-0 input: obs rows -> A tile (zero padded to kp8, zero rows past the batch); consecutive threads read
+  // consecutive floats of a row (coalesced), 4 floats per 16-byte core-matrix row
+  {
+    const int kq = p.layer[0].kp8 >> 2;  // 16-byte chunks per row
+    for (int id = tid; id < kTcRows * kq; id += kTcThreads) {
+      const int r = id / kq, c4 = id - r * kq;
+      const int row = row0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.n) {
+        const float *o = p.obs + (size_t)row * p.in_dim + 4 * c4;
+        const int k = 4 * c4;
+        v.x = k < p.in_dim ? __ldg(o) : 0.f;
+        v.y = k + 1 < p.in_dim ? __ldg(o + 1) : 0.f;
+        v.z = k + 2 < p.in_dim ? __ldg(o + 2) : 0.f;
+        v.w = k + 3 < p.in_dim ? __ldg(o + 3) : 0.f;
+      }
+      *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();  // tensor-memory address and mbarrier inits visible
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t a_base = tc_smem_u32(smA);
+
+  for (int c = 0; c < p.n_chunks; c++) {
+    const TcChunk &ch = p.chunk[c];
+    const int b = c % kTcBufs;
+    // copy thread: chunk c + 2 goes where chunk c - 1 was; wait until the MMAs that read it have been committed
+    if (tid == 32 && c + 2 < p.n_chunks) {
+      if (c >= 1) tc_mbar_wait(empty_bar((c - 1) % kTcBufs), (uint32_t)(((c - 1) / kTcBufs) & 1));
+      issue_chunk(c + 2);
+    }
+    if (ch.k0 == 0) {
+      // first chunk of a layer: the A tile was just written through the generic proxy (staging loop / previous
+      // epilogue) and the previous accumulators were just read from tensor memory
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+    }
+    const TcLayer &L = p.layer[ch.layer];
+    if (tid == 0) {  // the MMA thread
+      tc_mbar_wait(full_bar(b), (uint32_t)((c / kTcBufs) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t idesc = tc_instr_desc(L.np16);
+      const uint32_t b_base = tc_smem_u32(smB + b * kTcBBytes);
+      const uint32_t sbo_b = (uint32_t)(ch.kc >> 2) * 128u;
+      for (int j = 0; j < (ch.kc >> 3); j++) {
+        const uint64_t da = tc_smem_desc(a_base + (uint32_t)((ch.k0 + 8 * j) >> 2) * 128u, 128u, (uint32_t)kTcSboA);
+        const uint64_t db = tc_smem_desc(b_base + (uint32_t)j * 256u, 128u, sbo_b);
+        tc_mma(tmem, da, db, idesc, (ch.k0 + j) > 0 ? 1u : 0u);
+      }
+      tc_commit(empty_bar(b));
+      if (ch.last) tc_commit(done_bar);
+    }
+    if (ch.last) {
+      tc_mbar_wait(done_bar, (uint32_t)(ch.layer & 1));  // the layer's MMAs are complete
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool last = ch.layer == p.n_layers - 1;
+      const int q = warp & 3, h = warp >> 2;
+      const float *bias = p.bias[ch.layer];
+      switch (L.act) {
+        case PUPPER_ACT_RELU: tc_epilogue<PUPPER_ACT_RELU>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_SIGMOID: tc_epilogue<PUPPER_ACT_SIGMOID>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_ELU: tc_epilogue<PUPPER_ACT_ELU>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_TANH: tc_epilogue<PUPPER_ACT_TANH>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_SWISH: tc_epilogue<PUPPER_ACT_SWISH>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_GELU: tc_epilogue<PUPPER_ACT_GELU>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        case PUPPER_ACT_LEAKY_RELU: tc_epilogue<PUPPER_ACT_LEAKY_RELU>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+        default: tc_epilogue<PUPPER_ACT_LINEAR>(p, L, bias, last, tmem, smA, q, h, lane, row0); break;
+      }
+      // (the fences + CTA barrier at the first chunk of the next layer order these tensor-memory reads and A-tile
+      //  writes before that layer's MMAs)
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+constexpr int kTcSmemBytes = kTcABytes + kTcBufs * kTcBBytes + 64;
+
+// Host side: can this MLP run on the tcgen05 kernel, and its chunk table.
+struct TcPlan {
+  bool ok = false;
+  TcParams params;
+};
+
+}  // namespace pupper
