@@ -40,6 +40,8 @@ enum {
 
 /* Arithmetic of the matrix products (accumulation is always float32):
  *   PUPPER_POLICY_TF32   operands rounded to TF32 (what XLA's default float32 matmul precision does on this GPU class);
+ *                        layers up to 256 wide run on the tcgen05 / tensor-memory kernel (set PUPPER_POLICY_LEGACY=1 in the
+ *                        environment at create time to force the mma.sync kernel);
  *   PUPPER_POLICY_3XTF32 each product as three TF32 products of hi/lo splits: float32-level accuracy (default). */
 enum { PUPPER_POLICY_TF32 = 1, PUPPER_POLICY_3XTF32 = 3 };
 

@@ -58,10 +58,10 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 template <int ACT>
 __device__ __forceinline__ float policy_act(float x) {
   if (ACT == PUPPER_ACT_RELU) return fmaxf(x, 0.f);
-  if (ACT == PUPPER_ACT_SIGMOID) return __frcp_rn(1.f + __expf(-x));
+  if (ACT == PUPPER_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));  // ex2.approx + rcp.approx (no IEEE fix-up path)
   if (ACT == PUPPER_ACT_ELU) return x > 0.f ? x : expm1f(x);
   if (ACT == PUPPER_ACT_TANH) return tanhf(x);
-  if (ACT == PUPPER_ACT_SWISH) return x * __frcp_rn(1.f + __expf(-x));  // ex2.approx + rcp: ~1e-6 relative, far inside float32 policy noise
+  if (ACT == PUPPER_ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));  // ex2.approx + rcp.approx: ~1e-6 relative, far inside float32 policy noise
   if (ACT == PUPPER_ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
   if (ACT == PUPPER_ACT_LEAKY_RELU) return x > 0.f ? x : 0.01f * x;
   return x;
@@ -390,6 +390,12 @@ int pupper_policy_create(int n_layers, const int32_t *in_dims, const int32_t *ou
   *out = pol;
   return PUPPER_OK;
 }
+
+#ifdef PUPPER_TC_TRACE
+int pupper_policy_tc_trace(long long *host256) {
+  return cudaMemcpyFromSymbol(host256, pupper::g_tc_trace, 256 * sizeof(long long)) == cudaSuccess ? 0 : -3;
+}
+#endif
 
 int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, float *action, pupper_stream_t stream) {
   if (!policy || !obs || !action || n <= 0) return PUPPER_EINVAL;

@@ -32,6 +32,10 @@ constexpr int kTcMaxW = 256;             // widest layer input / output
 constexpr int kTcABytes = kTcRows * kTcMaxW * 4;   // 128 KB activation tile
 constexpr int kTcBBytes = 32 * 1024;     // one weight chunk buffer
 constexpr int kTcBufs = 3;               // ... of three: copies run two chunks ahead
+#ifndef PUPPER_TC_PIECES
+#define PUPPER_TC_PIECES 4
+#endif
+constexpr int kTcPieces = PUPPER_TC_PIECES;  // bulk-copy requests per chunk
 constexpr int kTcSboA = (kTcMaxW / 4) * 128;       // bytes between 8-row groups of the A tile
 constexpr int kTcMaxChunks = 32;
 
@@ -53,6 +57,12 @@ struct TcParams {
   float *action;
 };
 
+#ifdef PUPPER_TC_TRACE  // timeline of CTA 0 (clock64 stamps; slot layout in tools/tc_trace.py), exported through pupper_policy_tc_trace
+__device__ long long g_tc_trace[256];
+#define TC_STAMP(slot) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 64)) g_tc_trace[(slot) + (threadIdx.x ? 128 : 0)] = clock64(); } while (0)
+#else
+#define TC_STAMP(slot) ((void)0)
+#endif
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // K-major, no swizzle: start address, leading byte offset (between the two 16-byte K halves of one MMA), stride byte
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   // that skips their intermediate phases cannot tell phase k from phase k + 2 by parity.)
   const uint32_t done_bar = tc_smem_u32(&bars[2 * kTcBufs]);
 
+  TC_STAMP(0);
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -148,9 +159,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     const TcChunk &ch = p.chunk[c];
     const uint32_t dst = tc_smem_u32(smB + (c % kTcBufs) * kTcBBytes), bar = full_bar(c % kTcBufs);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)ch.bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(ch.src),
-                 "r"((uint32_t)ch.bytes), "r"(bar)
-                 : "memory");
+    // several requests per chunk: the copy engine overlaps them (one 32 KB request alone took ~3.3 k cycles)
+    const uint32_t piece = (uint32_t)ch.bytes / kTcPieces;  // chunk sizes are multiples of 512 bytes
+    const unsigned char *src = reinterpret_cast<const unsigned char *>(ch.src);
+#pragma unroll
+    for (int i = 0; i < kTcPieces; i++)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + i * piece),
+                   "l"(src + (size_t)i * piece), "r"(piece), "r"(bar)
+                   : "memory");
   };
   if (tid == 32) {  // the copy thread
     for (int b = 0; b < 2 * kTcBufs + 1; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[b])) : "memory");
@@ -159,22 +175,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     if (p.n_chunks > 1) issue_chunk(1);
   }
   // layer-0 input: obs rows -> A tile (zero padded to kp8, zero rows past the batch); consecutive threads read
-  // consecutive floats of a row (coalesced), 4 floats per 16-byte core-matrix row
+  // consecutive 16-byte pieces of a row (coalesced).  All loads of a pass are issued before the first store.
   {
     const int kq = p.layer[0].kp8 >> 2;  // 16-byte chunks per row
-    for (int id = tid; id < kTcRows * kq; id += kTcThreads) {
-      const int r = id / kq, c4 = id - r * kq;
-      const int row = row0 + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.n) {
-        const float *o = p.obs + (size_t)row * p.in_dim + 4 * c4;
-        const int k = 4 * c4;
-        v.x = k < p.in_dim ? __ldg(o) : 0.f;
-        v.y = k + 1 < p.in_dim ? __ldg(o + 1) : 0.f;
-        v.z = k + 2 < p.in_dim ? __ldg(o + 2) : 0.f;
-        v.w = k + 3 < p.in_dim ? __ldg(o + 3) : 0.f;
+    const bool vec = (p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
+    constexpr int U = 5;  // 128 rows x 72 floats = 2304 pieces = one pass of 5 per thread
+    for (int base = 0; base < kTcRows * kq; base += U * kTcThreads) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int id = base + u * kTcThreads + tid;
+        const int r = id / kq, c4 = id - r * kq, row = row0 + r, k = 4 * c4;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (id < kTcRows * kq && row < p.n) {
+          const float *o = p.obs + (size_t)row * p.in_dim + k;
+          if (vec && k + 3 < p.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(o));
+          else {
+            v[u].x = k < p.in_dim ? __ldg(o) : 0.f;
+            v[u].y = k + 1 < p.in_dim ? __ldg(o + 1) : 0.f;
+            v[u].z = k + 2 < p.in_dim ? __ldg(o + 2) : 0.f;
+            v[u].w = k + 3 < p.in_dim ? __ldg(o + 3) : 0.f;
+          }
+        }
       }
-      *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int id = base + u * kTcThreads + tid;
+        const int r = id / kq, c4 = id - r * kq;
+        if (id < kTcRows * kq) *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v[u];
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -182,6 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   const uint32_t a_base = tc_smem_u32(smA);
+  TC_STAMP(1);
 
   for (int c = 0; c < p.n_chunks; c++) {
     const TcChunk &ch = p.chunk[c];
@@ -201,20 +231,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
     const TcLayer &L = p.layer[ch.layer];
     if (tid == 0) {  // the MMA thread
       tc_mbar_wait(full_bar(b), (uint32_t)((c / kTcBufs) & 1));
+      TC_STAMP(8 + 4 * c);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t idesc = tc_instr_desc(L.np16);
-      const uint32_t b_base = tc_smem_u32(smB + b * kTcBBytes);
-      const uint32_t sbo_b = (uint32_t)(ch.kc >> 2) * 128u;
-      for (int j = 0; j < (ch.kc >> 3); j++) {
-        const uint64_t da = tc_smem_desc(a_base + (uint32_t)((ch.k0 + 8 * j) >> 2) * 128u, 128u, (uint32_t)kTcSboA);
-        const uint64_t db = tc_smem_desc(b_base + (uint32_t)j * 256u, 128u, sbo_b);
-        tc_mma(tmem, da, db, idesc, (ch.k0 + j) > 0 ? 1u : 0u);
+      // descriptors of k-step 0; each further k-step (8 columns = two 16-byte core-matrix columns) advances both start
+      // addresses by 256 bytes, i.e. the 14-bit address field (bytes >> 4) by 16 -- no carry out of the field below 256 KB
+      uint64_t da = tc_smem_desc(a_base + (uint32_t)(ch.k0 >> 2) * 128u, 128u, (uint32_t)kTcSboA);
+      uint64_t db = tc_smem_desc(tc_smem_u32(smB + b * kTcBBytes), 128u, (uint32_t)(ch.kc >> 2) * 128u);
+      const int nk = ch.kc >> 3;
+      tc_mma(tmem, da, db, idesc, ch.k0 > 0 ? 1u : 0u);
+#pragma unroll 4
+      for (int j = 1; j < nk; j++) {
+        da += 16; db += 16;
+        tc_mma(tmem, da, db, idesc, 1u);
       }
       tc_commit(empty_bar(b));
       if (ch.last) tc_commit(done_bar);
+      TC_STAMP(9 + 4 * c);
     }
     if (ch.last) {
       tc_mbar_wait(done_bar, (uint32_t)(ch.layer & 1));  // the layer's MMAs are complete
+      TC_STAMP(10 + 4 * c);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const bool last = ch.layer == p.n_layers - 1;
       const int q = warp & 3, h = warp >> 2;
@@ -231,6 +268,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
       }
       // (the fences + CTA barrier at the first chunk of the next layer order these tensor-memory reads and A-tile
       //  writes before that layer's MMAs)
+      TC_STAMP(11 + 4 * c);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -3,8 +3,9 @@
 The reference trains with Brax PPO (policy MLP in JAX).  JAX is unavailable here, so the policy is an MLP of the
 shape ``export.py`` describes (dense layers, observation normalisation folded into layer 0, tanh head) -- a labelled
 substitution -- evaluated either by this repo's fused tensor-core kernel (``impl="cuda"``, the default: one launch per forward
-pass, ``csrc/pupper_policy.cuh``; measured on B200 at 8192 rows: 51 us per call with float32-level accuracy
-(3xTF32), 36 us at TF32, against 83 us for the graph-replayed torch/cuBLAS layers) or by torch/cuBLAS
+pass; measured on B200 at 8192 rows: 48 us per call with float32-level accuracy (3xTF32, ``csrc/pupper_policy.cuh``),
+23 us at TF32 -- XLA's default float32 matmul precision on this GPU class -- on the tcgen05 / tensor-memory kernel
+(``csrc/pupper_policy_tc.cuh``), against 83 us for the graph-replayed torch/cuBLAS layers) or by torch/cuBLAS
 (``impl="torch"``, the float32 checker the tests compare against).  One unroll = ``unroll_length`` x (policy forward + fused env step); nothing synchronises
 with the host, so the whole unroll can be captured in a CUDA graph.
 """

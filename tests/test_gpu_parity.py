@@ -653,6 +653,40 @@ def test_rollout_with_cuda_policy_matches_torch_policy():
     col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=True)
     r1 = {k: v.clone() for k, v in col.collect().items()}
     assert torch.isfinite(r1["obs"]).all() and float(r1["action"].abs().max()) <= 1.0
+    # the TF32 policy runs on the tcgen05 kernel (tensor memory, bulk async copies): eager and graph-replayed unrolls from
+    # the same start state are bit-identical, and the first actions agree with the float32 policy to TF32 rounding
+    res = []
+    for use_graph in (False, True):
+        env = common.make_env()
+        tenv = wrappers.wrap(env, episode_length=1000)
+        st = tenv.reset(keys)
+        pol = rollout.PolicyMLP.random(env.observation_size, impl="cuda", precision=1)
+        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=use_graph)
+        if not use_graph:
+            col.collect()  # the graph twin ran one warm-up unroll at construction
+        res.append({k: v.clone() for k, v in col.collect().items()})
+    for k in ("obs", "action", "reward", "done"):
+        assert torch.equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.gpu
+def test_policy_tcgen05_path_is_used_and_matches_the_mma_sync_path(monkeypatch):
+    """TF32 mode: widths <= 256 go through the tcgen05 kernel, PUPPER_POLICY_LEGACY=1 forces the mma.sync kernel; both feed
+    the same raw float32 bits as TF32 operands and accumulate in float32, so they agree to accumulation-order rounding."""
+    import torch
+    from pupperv3_mjx_b200 import rollout
+    x = torch.randn((777, 72), device="cuda")
+    pol_tc = rollout.PolicyMLP.random(72, impl="cuda", precision=1, seed=5)
+    monkeypatch.setenv("PUPPER_POLICY_LEGACY", "1")
+    pol_legacy = rollout.PolicyMLP.random(72, impl="cuda", precision=1, seed=5)
+    monkeypatch.delenv("PUPPER_POLICY_LEGACY")
+    a, b = pol_tc(x), pol_legacy(x)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a).all()
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-4)  # TF32 rounding itself is ~1e-3
+    wide = rollout.PolicyMLP.random(540, hidden=(200, 64), impl="cuda", precision=1)  # 540-wide input: falls back to mma.sync, still correct
+    y = wide(torch.randn((65, 540), device="cuda"))
+    assert y.shape == (65, 12) and torch.isfinite(y).all()
 
 
 @pytest.mark.gpu
