@@ -345,19 +345,21 @@ def run_cuda(args):
         rand = functools.partial(dr.domain_randomize, rng=prng.split(prng.PRNGKey(2), en))
         tenv = wrappers.wrap(env_r, episode_length=1000, randomization_fn=rand)
         st = tenv.reset(torch.from_numpy(np.ascontiguousarray(prng.split(prng.PRNGKey(0), en)).view(np.int32)).to(dev))
-        col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env_r.observation_size), st, T, use_cuda_graph=True)
-        for _ in range(5):
-            col.collect()
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(10):
-            col.collect()
-        s1.record()
-        torch.cuda.synchronize()
-        extra["rollout_8192"] = {"value": en * T * 10 / (s0.elapsed_time(s1) * 1e-3), "unit": UNIT,
-                                 "note": "unroll 20, policy MLP 72-256-128-128-128-12 (stand-in for the JAX policy; fused 3xTF32 tensor-core kernel, "
-                                         "float32-level accuracy) + env step, one CUDA graph per unroll"}
+        for tag, prec, what in (("rollout_8192", 3, "fused 3xTF32 kernel (mma.sync), float32-level accuracy"),
+                                ("rollout_8192_tf32", 1, "TF32 on the tcgen05 / tensor-memory kernel (XLA's default float32 matmul precision)")):
+            col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env_r.observation_size, precision=prec), st, T, use_cuda_graph=True)
+            for _ in range(5):
+                col.collect()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                col.collect()
+            s1.record()
+            torch.cuda.synchronize()
+            extra[tag] = {"value": en * T * 10 / (s0.elapsed_time(s1) * 1e-3), "unit": UNIT,
+                          "note": f"configs[4] substitute: unroll 20, policy MLP 72-256-128-128-128-12 (stand-in for the JAX policy; {what}) "
+                                  "+ env step, one CUDA graph per unroll"}
         line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
