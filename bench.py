@@ -252,7 +252,7 @@ def run_cuda(args):
                    "envs_per_gpu": n, "settle_steps": args.settle, "l2": "NOT flushed (diagnostic run)" if args.no_flush else "flushed between timed steps (256 MB memset outside the event pairs)",
                    "timing": "mean of per-step CUDA event pairs on the launch stream, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic_4096 if n == 4096 else None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
+                     "traffic": traffic_4096 if n == 4096 else (9.2e7 if n == 65536 else None),  # 65536: 79.5 MB read + 12.5 MB written (same capture set) "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_alg(H),
                      "note": "the step is FP32-pipe/latency bound, not HBM bound (DESIGN.md); see fp32"},
         "fp32": {"flop_per_env_step": flop_per_step, "achieved_tflops": flop_per_step * value / world / 1e12,
                  "peak_tflops": ffma_peak, "peak_source": "measured in this run: FFMA probe kernel, 8 chains/thread, best of 5 (nominal 74.4)",

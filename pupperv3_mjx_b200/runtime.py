@@ -294,34 +294,43 @@ class EnvRuntime:
         self._chunk_cache = (key, self._dr_struct, out)
         return out
 
-    def step_host(self, h_action: torch.Tensor, h_out: torch.Tensor, chunks: Optional[int] = None) -> torch.cuda.Event:
+    def step_host(self, h_action: torch.Tensor, h_out: torch.Tensor, chunks: Optional[int] = None):
         """One env step with HOST buffers: ``h_action`` [n, 12] float32 (pinned) in, ``h_out`` = ``obs | reward | done``
-        (the ``packed_outputs`` layout, pinned) out.  Returns the event to wait on before reading ``h_out``.
+        (the ``packed_outputs`` layout, pinned) out.  Returns the object to ``.synchronize()`` on before reading ``h_out`` (the
+        caller's stream for one range, an event for the pipelined case).
 
         Large batches are cut into ``chunks`` contiguous env ranges that are pipelined over three streams (actions in,
         step kernels in order, observations out), so the PCIe transfers of one range overlap the kernel of the next: at
         65,536 envs the 19 MB of observations per step cost about as much as the step itself.  Small batches (the step
         is latency bound and would not get shorter by splitting) take one chunk on the current stream."""
-        n, H = self.n_envs, self.cfg.observation_history
-        w = H * abi.OBS_DIM
-        if self.guard_rows or self.dbg:
-            raise PupperError("step_host is the production path: no guard rows, no debug taps")
+        n = self.n_envs
+        w = self.cfg.observation_history * abi.OBS_DIM
         if h_action.dtype != torch.float32 or h_action.numel() != n * abi.NU or h_out.dtype != torch.float32 or h_out.numel() != n * (w + 2):
             raise PupperError("h_action must be float32 [n_envs, 12] and h_out float32 [n_envs * (H*36 + 2)]")
         if chunks is None:
             chunks = max(1, min(8, n // 16384))
         if not hasattr(self, "_d_act"):
+            if self.guard_rows or self.dbg:
+                raise PupperError("step_host is the production path: no guard rows, no debug taps")
             self._d_act = torch.empty((n, abi.NU), dtype=torch.float32, device=self.device)
             self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
             self._done_ev = torch.cuda.Event()
         cur = torch.cuda.current_stream(self.device)
-        done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
         if chunks <= 1:
+            # latency path: three enqueues on the caller's stream; the stream itself is the thing to wait on
+            if torch.cuda.current_device() != self.device_index:  # rare: the caller works on another device
+                with torch.cuda.device(self.device):
+                    return self.step_host(h_action, h_out, chunks)
             self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
-            self.step(self._d_act)
+            rc = self.lib.pupper_step(self._model, n, C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
+                                      self._d_act.data_ptr(), C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                      cur.cuda_stream)
+            if rc != 0:
+                _check(self.lib, rc, "pupper_step")
+            self.launches += 1
             h_out.copy_(self._out_pack, non_blocking=True)
-            done_ev.record(cur)
-            return done_ev
+            return cur
+        done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
         ha, flat = h_action.view(n, abi.NU), h_out.view(-1)
         self._s_in.wait_stream(cur)
         self._s_out.wait_stream(cur)

@@ -22,3 +22,18 @@ for chunks in chunk_list:
     for t in range(100): rt.step_host(h_act[t % 4], h_out, chunks=chunks).synchronize()
     dt = (time.perf_counter() - t0) / 100
     print(f"n={n} chunks={chunks}: {dt * 1e3:.4f} ms/step -> {n / dt:.4g} env-steps/s end to end")
+# the same loop written out by hand (copy, step, copy, stream sync), for comparison with step_host at one range
+d_act = torch.empty((n, 12), device="cuda")
+for t in range(5):
+    d_act.copy_(h_act[t % 4], non_blocking=True); rt.step(d_act); h_out.copy_(rt.packed_outputs(), non_blocking=True); torch.cuda.current_stream().synchronize()
+t0 = time.perf_counter()
+for t in range(100):
+    d_act.copy_(h_act[t % 4], non_blocking=True); rt.step(d_act); h_out.copy_(rt.packed_outputs(), non_blocking=True); torch.cuda.current_stream().synchronize()
+dt = (time.perf_counter() - t0) / 100
+print(f"n={n} hand-written loop: {dt * 1e3:.4f} ms/step -> {n / dt:.4g} env-steps/s end to end")
+t0 = time.perf_counter()
+for t in range(100):
+    rt.step(d_act)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / 100
+print(f"n={n} device-only back-to-back steps: {dt * 1e3:.4f} ms/step")
