@@ -114,6 +114,18 @@ class PipelineStateView:
         raise NotImplementedError("sensors are never read by the env (SURVEY.md P11) and are not computed")
 
 
+def env_ranges(n: int, chunks: int, wave: int):
+    """Contiguous env ranges ``[(first, count), ...]`` covering ``n`` envs in about ``chunks`` pieces for the pipelined host
+    path.  A range is a whole number of kernel waves (``wave`` = envs the GPU runs at once: 2 CTAs of 32 envs per SM) when
+    the batch is that large, so cutting the batch does not add partially filled waves; otherwise a multiple of 32 envs (the
+    SoA rows stay 128-byte aligned either way)."""
+    if n <= 0 or chunks <= 0:
+        raise ValueError("n and chunks must be positive")
+    size = (n + chunks - 1) // chunks
+    size = (size + wave - 1) // wave * wave if size >= wave else (size + 31) // 32 * 32
+    return [(e0, min(size, n - e0)) for e0 in range(0, n, size)]
+
+
 class EnvRuntime:
     def __init__(self, model_desc: abi.PupperModelDesc, env_cfg: abi.PupperEnvCfg, n_envs: int, device: int = 0,
                  episode: bool = False, debug: bool = False, guard_rows: int = 0):
@@ -260,14 +272,9 @@ class EnvRuntime:
         if getattr(self, "_chunk_cache", None) and self._chunk_cache[0] == key and self._chunk_cache[1] is self._dr_struct:
             return self._chunk_cache[2]
         n, H = self.n_envs, self.cfg.observation_history
-        # range size: a whole number of kernel waves (2 CTAs of 32 envs per SM) when the batch is that large, so cutting the
-        # batch does not add partially filled waves; otherwise a multiple of 32 envs
         wave = torch.cuda.get_device_properties(self.device).multi_processor_count * 2 * 32
-        size = (n + chunks - 1) // chunks
-        size = (size + wave - 1) // wave * wave if size >= wave else (size + 31) // 32 * 32
         out = []
-        for e0 in range(0, n, size):
-            cnt = min(size, n - e0)
+        for e0, cnt in env_ranges(n, chunks, wave):
             st = abi.PupperState()
             st.stride = self.stride
             for name in abi.STATE_FIELDS:

@@ -144,3 +144,23 @@ def test_system_tree_replace():
     s2 = s.tree_replace({"opt.timestep": 0.004, "body_mass": s.body_mass * 2})
     assert s2.timestep == 0.004 and np.allclose(s2.body_mass, 2 * s.body_mass) and not s2.is_batched()
     assert s.jnt_range.shape == (13, 2)
+
+
+def test_env_ranges_of_the_pipelined_host_path():
+    """runtime.env_ranges: the ranges tile [0, n) without gaps or overlap, start on multiples of 32 envs (128-byte aligned
+    SoA rows), are whole kernel waves when the batch is large, and never exceed the requested count by more than rounding."""
+    from pupperv3_mjx_b200.runtime import env_ranges
+    wave = 148 * 2 * 32
+    for n in (1, 31, 32, 333, 4096, 16384, 65536, 65537, 100000):
+        for chunks in (1, 2, 3, 4, 5, 7, 8):
+            r = env_ranges(n, chunks, wave)
+            assert r[0][0] == 0 and sum(c for _, c in r) == n
+            for (a, ca), (b, _) in zip(r, r[1:]):
+                assert a + ca == b
+            assert all(e0 % 32 == 0 for e0, _ in r) and all(c > 0 for _, c in r)
+            assert len(r) <= chunks
+            if n // chunks >= wave:
+                assert all(c % wave == 0 for _, c in r[:-1])
+    assert env_ranges(65536, 4, wave) == [(0, 18944), (18944, 18944), (37888, 18944), (56832, 8704)]
+    with pytest.raises(ValueError):
+        env_ranges(0, 1, wave)
