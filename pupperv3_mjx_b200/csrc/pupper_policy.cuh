@@ -289,6 +289,7 @@ struct PupperPolicy {
   int device, precision, smem_bytes;
   std::vector<void *> allocs;
   bool use_tc = false;          // TF32 mode on the tcgen05 kernel (every layer width <= 256)
+  bool tc_v2 = false;           // PUPPER_POLICY_TC2 at create time: the warp-specialised tcgen05 kernel (measured equal at 8192 rows, +3 % at 65536)
   pupper::TcParams tc;
 };
 
@@ -380,6 +381,8 @@ int pupper_policy_create(int n_layers, const int32_t *in_dims, const int32_t *ou
     if (fits) {
       T.n_chunks = nchunk; T.n_layers = n_layers; T.in_dim = in_dims[0];
       e = cudaFuncSetAttribute(pupper::policy_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pupper::kTcSmemBytes);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::policy_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pupper::kTcSmemBytes);
+      pol->tc_v2 = getenv("PUPPER_POLICY_TC2") != nullptr;
       if (e != cudaSuccess) { pupper_policy_destroy(pol); return cuda_fail(e, "cudaFuncSetAttribute(policy_tc_kernel)"); }
       pol->use_tc = true;
     }
@@ -406,7 +409,9 @@ int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, f
   if (policy->use_tc) {
     pupper::TcParams t = policy->tc;
     t.n = n; t.obs = obs; t.action = action;
-    pupper::policy_tc_kernel<<<(n + pupper::kTcRows - 1) / pupper::kTcRows, pupper::kTcThreads, pupper::kTcSmemBytes, s>>>(t);
+    const int grid = (n + pupper::kTcRows - 1) / pupper::kTcRows;
+    if (policy->tc_v2) pupper::policy_tc2_kernel<<<grid, pupper::kTc2Threads, pupper::kTcSmemBytes, s>>>(t);
+    else pupper::policy_tc_kernel<<<grid, pupper::kTcThreads, pupper::kTcSmemBytes, s>>>(t);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "policy_tc_kernel launch");
     return PUPPER_OK;

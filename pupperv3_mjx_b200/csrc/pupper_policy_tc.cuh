@@ -60,8 +60,10 @@ struct TcParams {
 #ifdef PUPPER_TC_TRACE  // timeline of CTA 0 (clock64 stamps; slot layout in tools/tc_trace.py), exported through pupper_policy_tc_trace
 __device__ long long g_tc_trace[256];
 #define TC_STAMP(slot) do { if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 64)) g_tc_trace[(slot) + (threadIdx.x ? 128 : 0)] = clock64(); } while (0)
+#define TC_STAMP2(slot, second) do { if (blockIdx.x == 0) g_tc_trace[(slot) + ((second) ? 128 : 0)] = clock64(); } while (0)
 #else
 #define TC_STAMP(slot) ((void)0)
+#define TC_STAMP2(slot, second) ((void)0)
 #endif
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -111,9 +113,11 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // Epilogue of one layer for this warp: quadrant q (rows 32 q + lane), 16-column groups h, h + 2, ...
+// `ready0` != 0 (warp-specialised kernel): after a group's 16 columns are in the A tile the warp arrives on the group's
+// mbarrier (ready0 + 8 g), so the MMA warp can start the next layer's k-steps on those columns at once.
 template <int ACT>
 __device__ __forceinline__ void tc_epilogue(const TcParams &p, const TcLayer &L, const float *bias, bool last, uint32_t tmem, unsigned char *smA,
-                                            int q, int h, int lane, int row0) {
+                                            int q, int h, int lane, int row0, uint32_t ready0 = 0u) {
   const int r = 32 * q + lane;
   unsigned char *arow = smA + (r & 7) * 16 + (r >> 3) * kTcSboA;
   const int row = row0 + r;
@@ -127,6 +131,12 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, const TcLayer &L,
 #pragma unroll
       for (int i = 0; i < 4; i++)
         *reinterpret_cast<float4 *>(arow + ((c0 >> 2) + i) * 128) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if (ready0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // A-tile stores -> visible to the tensor core's proxy
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");    // this warp's tensor-memory reads are complete
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ready0 + 8u * g) : "memory");
+      }
     } else if (row < p.n) {
 #pragma unroll
       for (int i = 0; i < 16; i++)
@@ -276,7 +286,162 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
 }
 
-constexpr int kTcSmemBytes = kTcABytes + kTcBufs * kTcBBytes + 64;
+// ---- warp-specialised variant ---------------------------------------------------------------------------------------
+// 16 epilogue warps + one MMA warp + one copy warp.  The accumulators are double buffered in tensor memory (512 columns:
+// layer l uses columns 256 (l & 1) ...), and the epilogue hands the next layer's A tile over in 16-column groups, each
+// with its own mbarrier (4 arrivals: the group's four quadrant warps), so the MMA warp issues the k-steps of layer l + 1
+// while the epilogue of layer l is still producing the later columns.
+// Measured (tools/tc_trace2.py): the overlap happens, but it does not shorten the chain -- TF32 MMAs at N = 128 read their
+// operands from shared memory at ~122 of the 128 B/clk, so the epilogue's A-tile stores and the concurrent MMAs slow each
+// other down (a 16-column group takes 2.2 k cycles instead of 1.3 k): 22.7 us at 8192 rows either way, 82 vs 84.5 us at
+// 65,536 rows.  Opt-in (PUPPER_POLICY_TC2=1 at create time) until the operands move to a swizzled layout.
+constexpr int kTc2Threads = kTcThreads + 64;
+constexpr int kTcGroups = kTcMaxW / 16;
+__global__ void __launch_bounds__(kTc2Threads, 1) policy_tc2_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem[];
+  unsigned char *smA = tc_smem;
+  unsigned char *smB = tc_smem + kTcABytes;
+  // full[3], empty[3], done[2], staged, ready[16]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(tc_smem + kTcABytes + kTcBufs * kTcBBytes);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * kTcBufs + 3 + kTcGroups);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kTcRows;
+  auto full_bar = [&](int b) { return tc_smem_u32(&bars[b]); };
+  auto empty_bar = [&](int b) { return tc_smem_u32(&bars[kTcBufs + b]); };
+  auto done_bar = [&](int l) { return tc_smem_u32(&bars[2 * kTcBufs + (l & 1)]); };
+  const uint32_t staged_bar = tc_smem_u32(&bars[2 * kTcBufs + 2]);
+  const uint32_t ready0 = tc_smem_u32(&bars[2 * kTcBufs + 3]);
+  constexpr int kMmaWarp = kTcThreads / 32, kCopyWarp = kMmaWarp + 1;
+
+  if (tid == kMmaWarp * 32) TC_STAMP2(0, false);
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tc_smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == kCopyWarp * 32) {
+    for (int b = 0; b < 2 * kTcBufs + 2; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc_smem_u32(&bars[b])) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(staged_bar), "r"(kTcThreads / 32) : "memory");
+    for (int g = 0; g < kTcGroups; g++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(ready0 + 8u * g) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();  // tensor-memory address and mbarrier inits visible
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kCopyWarp) {
+    if (lane == 0) {
+      for (int c = 0; c < p.n_chunks; c++) {
+        const TcChunk &ch = p.chunk[c];
+        const int b = c % kTcBufs;
+        if (c >= kTcBufs) tc_mbar_wait(empty_bar(b), (uint32_t)(((c / kTcBufs) - 1) & 1));  // the MMAs that read this buffer are done
+        const uint32_t dst = tc_smem_u32(smB + b * kTcBBytes), bar = full_bar(b);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)ch.bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(ch.src),
+                     "r"((uint32_t)ch.bytes), "r"(bar)
+                     : "memory");
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t a_base = tc_smem_u32(smA);
+      uint32_t ready_phase = 0u;  // bit g: parity of the next completion of group g's barrier
+      for (int c = 0; c < p.n_chunks; c++) {
+        const TcChunk &ch = p.chunk[c];
+        const TcLayer &L = p.layer[ch.layer];
+        const int b = c % kTcBufs;
+        if (ch.layer == 0) {
+          if (ch.k0 == 0) tc_mbar_wait(staged_bar, 0u);
+        } else {
+          for (int g = ch.k0 >> 4; g <= ((ch.k0 + ch.kc - 1) >> 4); g++) {  // this chunk's columns of the A tile are in place
+            if (((ch.k0 >> 4) == g && (ch.k0 & 15) != 0)) continue;        // group already waited for by the previous chunk
+            tc_mbar_wait(ready0 + 8u * g, (ready_phase >> g) & 1u);
+            ready_phase ^= 1u << g;
+          }
+        }
+        TC_STAMP2(10 + 4 * c, false);  // A columns ready
+        tc_mbar_wait(full_bar(b), (uint32_t)((c / kTcBufs) & 1));
+        TC_STAMP2(8 + 4 * c, false);   // weights seen
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t idesc = tc_instr_desc(L.np16);
+        const uint32_t d_tmem = tmem + (uint32_t)(ch.layer & 1) * 256u;
+        uint64_t da = tc_smem_desc(a_base + (uint32_t)(ch.k0 >> 2) * 128u, 128u, (uint32_t)kTcSboA);
+        uint64_t db = tc_smem_desc(tc_smem_u32(smB + b * kTcBBytes), 128u, (uint32_t)(ch.kc >> 2) * 128u);
+        const int nk = ch.kc >> 3;
+        tc_mma(d_tmem, da, db, idesc, ch.k0 > 0 ? 1u : 0u);
+#pragma unroll 4
+        for (int j = 1; j < nk; j++) {
+          da += 16; db += 16;
+          tc_mma(d_tmem, da, db, idesc, 1u);
+        }
+        tc_commit(empty_bar(b));
+        if (ch.last) tc_commit(done_bar(ch.layer));
+        TC_STAMP2(9 + 4 * c, false);   // MMAs issued
+      }
+    }
+  } else {
+    // ---- epilogue warps: stage the layer-0 input, then one epilogue per layer ------------------------------------------
+    {
+      const int kq = p.layer[0].kp8 >> 2;  // 16-byte chunks per row
+      const bool vec = (p.in_dim & 3) == 0 && (reinterpret_cast<uintptr_t>(p.obs) & 15) == 0;
+      constexpr int U = 5;
+      for (int base = 0; base < kTcRows * kq; base += U * kTcThreads) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int id = base + u * kTcThreads + tid;
+          const int r = id / kq, c4 = id - r * kq, row = row0 + r, k = 4 * c4;
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (id < kTcRows * kq && row < p.n) {
+            const float *o = p.obs + (size_t)row * p.in_dim + k;
+            if (vec && k + 3 < p.in_dim) v[u] = __ldg(reinterpret_cast<const float4 *>(o));
+            else {
+              v[u].x = k < p.in_dim ? __ldg(o) : 0.f;
+              v[u].y = k + 1 < p.in_dim ? __ldg(o + 1) : 0.f;
+              v[u].z = k + 2 < p.in_dim ? __ldg(o + 2) : 0.f;
+              v[u].w = k + 3 < p.in_dim ? __ldg(o + 3) : 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const int id = base + u * kTcThreads + tid;
+          const int r = id / kq, c4 = id - r * kq;
+          if (id < kTcRows * kq) *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v[u];
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(staged_bar) : "memory");
+    }
+    const int q = warp & 3, h = warp >> 2;
+    for (int l = 0; l < p.n_layers; l++) {
+      const TcLayer &L = p.layer[l];
+      tc_mbar_wait(done_bar(l), (uint32_t)((l >> 1) & 1));  // the layer's MMAs are complete
+      if (tid == 64) TC_STAMP2(8 + 4 * l, true);   // layer done seen
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const bool last = l == p.n_layers - 1;
+      const float *bias = p.bias[l];
+      const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 256u;
+      switch (L.act) {
+        case PUPPER_ACT_RELU: tc_epilogue<PUPPER_ACT_RELU>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_SIGMOID: tc_epilogue<PUPPER_ACT_SIGMOID>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_ELU: tc_epilogue<PUPPER_ACT_ELU>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_TANH: tc_epilogue<PUPPER_ACT_TANH>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_SWISH: tc_epilogue<PUPPER_ACT_SWISH>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_GELU: tc_epilogue<PUPPER_ACT_GELU>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        case PUPPER_ACT_LEAKY_RELU: tc_epilogue<PUPPER_ACT_LEAKY_RELU>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+        default: tc_epilogue<PUPPER_ACT_LINEAR>(p, L, bias, last, d_tmem, smA, q, h, lane, row0, ready0); break;
+      }
+      if (tid == 64) TC_STAMP2(9 + 4 * l, true);   // epilogue done
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+constexpr int kTcSmemBytes = kTcABytes + kTcBufs * kTcBBytes + 256;
 
 // Host side: can this MLP run on the tcgen05 kernel, and its chunk table.
 struct TcPlan {

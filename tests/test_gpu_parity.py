@@ -680,10 +680,16 @@ def test_policy_tcgen05_path_is_used_and_matches_the_mma_sync_path(monkeypatch):
     monkeypatch.setenv("PUPPER_POLICY_LEGACY", "1")
     pol_legacy = rollout.PolicyMLP.random(72, impl="cuda", precision=1, seed=5)
     monkeypatch.delenv("PUPPER_POLICY_LEGACY")
-    a, b = pol_tc(x), pol_legacy(x)
+    monkeypatch.setenv("PUPPER_POLICY_TC2", "1")  # the warp-specialised variant (double-buffered tensor memory, per-group hand-over)
+    pol_tc2 = rollout.PolicyMLP.random(72, impl="cuda", precision=1, seed=5)
+    monkeypatch.delenv("PUPPER_POLICY_TC2")
+    a, b, c = pol_tc(x), pol_legacy(x), pol_tc2(x)
     torch.cuda.synchronize()
     assert torch.isfinite(a).all()
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-4)  # TF32 rounding itself is ~1e-3
+    assert torch.equal(a, c)  # same MMAs in the same order
+    for _ in range(20):       # repeated launches: the mbarrier phases of every call start from scratch
+        assert torch.equal(pol_tc2(x), c)
     wide = rollout.PolicyMLP.random(540, hidden=(200, 64), impl="cuda", precision=1)  # 540-wide input: falls back to mma.sync, still correct
     y = wide(torch.randn((65, 540), device="cuda"))
     assert y.shape == (65, 12) and torch.isfinite(y).all()

@@ -74,6 +74,14 @@ input staging, then per layer [weights seen -> MMAs issued -> layer done -> epil
 (`tcgen05.ld` -> bias -> swish -> 16-byte stores into the next layer's A tile) are MUFU bound (ex2 + rcp per element) and take
 ~15 k; the rest is single-thread issue overhead between chunks and the CTA barrier per layer.  At 65,536 rows (512 CTAs,
 3.5 waves) the kernel runs at 133 TFLOP/s of TF32 products.
+
+A warp-specialised variant (`policy_tc2_kernel`, opt-in with `PUPPER_POLICY_TC2=1`: 16 epilogue warps + MMA warp + copy warp,
+accumulators double buffered in tensor memory, the A tile handed over in 16-column groups through per-group mbarriers)
+overlaps the epilogue of layer l with the MMAs of layer l + 1 (`tools/tc_trace2.py`), but the call is not shorter:
+22.7 us at 8192 rows either way, 82 vs 84.5 us at 65,536 rows.  The no-swizzle TF32 MMAs at N = 128 already take ~122 of
+the 128 B/clk of shared-memory bandwidth, so the epilogue's A-tile stores and the concurrent MMAs slow each other down
+(a 16-column group takes 2.2 k cycles instead of 1.3 k).  A swizzled operand layout is the prerequisite for the overlap
+to pay.
 """
 open(os.path.join(P, "r1_policy.md"), "w").write(md)
 print(md[:1500])
