@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
 // Measured (tools/tc_trace2.py): the overlap happens, but it does not shorten the chain -- TF32 MMAs at N = 128 read their
 // operands from shared memory at ~122 of the 128 B/clk, so the epilogue's A-tile stores and the concurrent MMAs slow each
 // other down (a 16-column group takes 2.2 k cycles instead of 1.3 k): 22.7 us at 8192 rows either way, 82 vs 84.5 us at
-// 65,536 rows.  Opt-in (PUPPER_POLICY_TC2=1 at create time) until the operands move to a swizzled layout.
+// 65,536 rows.  Opt-in (PUPPER_POLICY_TC2=1 at create time) until the MMAs need less shared-memory traffic (A operand from
+// tensor memory, or a swizzled layout if the no-swizzle reads conflict).
 constexpr int kTc2Threads = kTcThreads + 64;
 constexpr int kTcGroups = kTcMaxW / 16;
 __global__ void __launch_bounds__(kTc2Threads, 1) policy_tc2_kernel(const __grid_constant__ TcParams p) {

@@ -80,8 +80,8 @@ accumulators double buffered in tensor memory, the A tile handed over in 16-colu
 overlaps the epilogue of layer l with the MMAs of layer l + 1 (`tools/tc_trace2.py`), but the call is not shorter:
 22.7 us at 8192 rows either way, 82 vs 84.5 us at 65,536 rows.  The no-swizzle TF32 MMAs at N = 128 already take ~122 of
 the 128 B/clk of shared-memory bandwidth, so the epilogue's A-tile stores and the concurrent MMAs slow each other down
-(a 16-column group takes 2.2 k cycles instead of 1.3 k).  A swizzled operand layout is the prerequisite for the overlap
-to pay.
+(a 16-column group takes 2.2 k cycles instead of 1.3 k).  The overlap will pay once the MMAs need less shared-memory
+traffic: the A operand from tensor memory (`tcgen05.mma` with A in TMEM), or a swizzled layout if the no-swizzle reads conflict.
 """
 open(os.path.join(P, "r1_policy.md"), "w").write(md)
 print(md[:1500])
