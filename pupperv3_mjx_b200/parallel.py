@@ -33,6 +33,32 @@ def allreduce_episode_totals(totals: torch.Tensor, group=None) -> torch.Tensor:
     return totals
 
 
+class EpisodeMetricsReducer:
+    """The path's only collective: every rank's kernel adds the sums of its COMPLETED episodes to a
+    24-float device accumulator; ``reduce()`` moves that interval's sums out of the accumulator, SUM-all-reduces them over
+    the ranks and adds the result to ``global_totals`` (float64, replicated).  Everything is enqueued on the current
+    stream (the accumulator is zeroed after the snapshot, in stream order with the step kernels), nothing synchronises
+    with the host.  Without a process group (one GPU) the all-reduce is skipped and the sums are just moved."""
+
+    def __init__(self, local_totals: torch.Tensor, group=None):
+        self.local = local_totals
+        self.group = group
+        self._buf = torch.zeros_like(local_totals)
+        self.global_totals = torch.zeros(local_totals.shape, dtype=torch.float64, device=local_totals.device)
+        self.n_reduces = 0
+
+    def reduce(self) -> torch.Tensor:
+        self._buf.copy_(self.local)
+        self.local.zero_()
+        allreduce_episode_totals(self._buf, self.group)
+        self.global_totals.add_(self._buf)
+        self.n_reduces += 1
+        return self.global_totals
+
+    def report(self) -> Dict[str, float]:
+        return episode_report(self.global_totals)
+
+
 def episode_report(totals: torch.Tensor) -> Dict[str, float]:
     """Per-episode means from the (all-reduced) accumulator, named like Brax's ``episode_metrics``."""
     t = totals.detach().float().cpu().numpy()

@@ -22,8 +22,15 @@ WORKER = textwrap.dedent('''
     totals[1] = 10.0 * (1 + rank)   # their summed reward
     totals[2] = 100.0 * (1 + rank)
     totals[3:22] = float(rank)
-    parallel.allreduce_episode_totals(totals)
-    rep = parallel.episode_report(totals)
+    red = parallel.EpisodeMetricsReducer(totals)
+    red.reduce()                       # interval 1: moves the local sums out, all-reduces them
+    assert float(totals.abs().sum()) == 0.0
+    red.reduce()                       # interval 2: nothing finished -> nothing is counted twice
+    totals[0] = 1.0; totals[1] = 5.0 * (1 + rank)   # interval 3: one more episode per rank
+    red.reduce()
+    g = red.global_totals.clone(); g[0] -= world; g[1] -= 5.0 * world * (world + 1) / 2
+    rep = parallel.episode_report(g)
+    rep["n_reduces"] = red.n_reduces
     gathered = [None] * world
     dist.all_gather_object(gathered, keys.tolist())
     if rank == 0:
@@ -53,6 +60,6 @@ def test_two_rank_allreduce_and_sharding(tmp_path):
     res = json.loads(line[len("RESULT "):])
     rep = res["rep"]
     assert rep["episodes"] == 3.0 and abs(rep["sum_reward"] - 10.0) < 1e-6 and abs(rep["length"] - 100.0) < 1e-6
-    assert abs(rep["total_dist"] - 1.0 / 3.0) < 1e-6
+    assert abs(rep["total_dist"] - 1.0 / 3.0) < 1e-6 and rep["n_reduces"] == 3
     keys = np.array(res["keys"][0] + res["keys"][1], dtype=np.uint32)
     np.testing.assert_array_equal(keys, prng.split(prng.PRNGKey(0), 37))
