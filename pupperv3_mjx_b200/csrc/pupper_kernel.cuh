@@ -96,7 +96,6 @@ struct EnvShared {
   uint32_t lv_cmd_rng[2];
   float sph[8][3];
   ContactSlot con[kMaxCon];
-  float conW[kMaxCon][5];  // per contact: W00, W01, W02, W11, W22 of the contact-frame Hessian block
   int ncon;
 };
 
@@ -428,14 +427,10 @@ __device__ __forceinline__ bool in_bracket(const LSPoint &x, const LSPoint &y) {
   return (((x.d0 < y.d0) & (y.d0 < 0.f)) | ((x.d0 > y.d0) & (y.d0 > 0.f))) != 0;  // bitwise: no short-circuit branches
 }
 
-// Row scalars of every active contact for this lane's pyramid edge: out[n][c] = (Jn + esgn*mu*Jt) . v_n
-// for N generalized vectors at once (v = [vb (6, replicated) | vl (this leg's 3)]).  Written to shared
-// memory at out[(n*kMaxCon + c)*kBlock].
+// Spatial velocity of this leg's link2 (depth 1) under each of N generalized vectors v = [vb (6, replicated) | vl (this
+// leg's 3)]; link3 adds vl[2]*cd[2].
 template <int N>
-__device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int k, const S6 cd[3], const V3 ba[3], const V3 bo[3],
-                                             const float (&vb)[N][6], const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int qbase, int ncon_w,
-                                             int part_all, bool ss_w, float *out) {
-  S6 W1[N];  // spatial velocity of this leg's link2 (depth 1) under v_n; link3 adds vl[2]*cd[2]
+__device__ __forceinline__ void link2_velocity(const S6 cd[3], const V3 ba[3], const V3 bo[3], const float (&vb)[N][6], const float (&vl)[N][3], S6 (&W1)[N]) {
 #pragma unroll
   for (int n = 0; n < N; n++) {
     S6 W0;
@@ -443,38 +438,92 @@ __device__ __forceinline__ void contact_rows(const EnvShared &es, int ncon, int 
     W0.l = V3{vb[n][0], vb[n][1], vb[n][2]} + vb[n][3] * bo[0] + vb[n][4] * bo[1] + vb[n][5] * bo[2];
     W1[n] = fma6(vl[n][1], cd[1], fma6(vl[n][0], cd[0], W0));
   }
+}
+
+// Constraint-row scalars J.v of the world-vs-leg contacts, computed by the lane whose leg touches ("own" contacts): that
+// lane has the chain's cdofs, so it evaluates the contact-point velocity once and derives all FOUR pyramid-edge rows
+// (Jn +- mu Jt1, Jn +- mu Jt2) from it; the trip count is the warp-wide maximum of contacts per LEG (1-2), not of contacts
+// per env.  The rows land in shared memory in the edge-per-lane layout the rest of the solver reads:
+// row of edge e of contact c at out[c*kBlock + e], with `out` pointing at lane 0 of this quad.
+// COST (N == 3, vectors = qvel, warm start, qacc_smooth): rows 1 and 2 are stored as Jaref = J.x - aref (buffers B, C)
+// and the constraint cost at both start points is accumulated in cw / cs; row 0 only feeds aref.
+// !COST (N == 1): the row is stored in buffer A.
+template <int N, bool COST>
+__device__ __forceinline__ void contact_rows_own(const EnvShared &es, const S6 cd[3], const V3 ba[3], const V3 bo[3], const float (&vb)[N][6],
+                                                 const float (&vl)[N][3], int own_list, int own_count, int nown_w, int part_all, float *out,
+                                                 float &cw, float &cs) {
+  S6 W1[N];
+  link2_velocity<N>(cd, ba, bo, vb, vl, W1);
 #pragma unroll 1
-  for (int c = 0; c < ncon_w; c++) {  // ncon_w: warp-wide maximum, so the shuffles below stay convergent
+  for (int i = 0; i < nown_w; i++) {  // warp-uniform trip count; lanes with fewer contacts sit the iteration out
+    if (i < own_count) {
+      const int c = (own_list >> (3 * i)) & 7;
+      const ContactSlot &s = es.con[c];
+      const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+      const int pc = (part_all >> (4 * c)) & 15;
+      const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
+      const float sg = d2 ? 1.f : -1.f;  // + as body2, - as body1
+      const float mu = s.mu;
+      float row[N][4];
+#pragma unroll
+      for (int n = 0; n < N; n++) {
+        const S6 W = fma6(dep == 2 ? vl[n][2] : 0.f, cd[2], W1[n]);
+        V3 pv = W.l + cross(W.a, r);  // velocity of the contact point as carried by the touching link
+        pv = V3{sg * pv.x, sg * pv.y, sg * pv.z};
+        const float jn = s.frame[0] * pv.x + s.frame[1] * pv.y + s.frame[2] * pv.z;
+        const float jt1 = s.frame[3] * pv.x + s.frame[4] * pv.y + s.frame[5] * pv.z;
+        const float jt2 = s.frame[6] * pv.x + s.frame[7] * pv.y + s.frame[8] * pv.z;
+        row[n][0] = fmaf(mu, jt1, jn); row[n][1] = fmaf(-mu, jt1, jn); row[n][2] = fmaf(mu, jt2, jn); row[n][3] = fmaf(-mu, jt2, jn);
+      }
+      float *o = out + c * kBlock;
+      if (COST) {
+        const float b = s.b, kimp = s.kimp, hD = 0.5f * s.D;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float aref = -b * row[0][e] - kimp;
+          const float xw = row[N > 1 ? 1 : 0][e] - aref, xs = row[N > 2 ? 2 : 0][e] - aref;
+          o[kMaxCon * kBlock + e] = xw; o[2 * kMaxCon * kBlock + e] = xs;  // Jaref at the warm start / at qacc_smooth
+          const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
+          cw = fmaf(hD * mw, mw, cw);
+          cs = fmaf(hD * ms, ms, cs);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[e] = row[0][e];
+      }
+    }
+  }
+}
+
+// Same rows for LEG-LEG contacts (rare): two legs carry the contact point, so every lane evaluates ITS pyramid edge of
+// the slot and the two legs' contributions are summed over the quad.  Walks the slots of `slots_w` (warp-uniform: slots
+// holding a leg-leg contact in some env of the warp) and writes those that are leg-leg in this env (`slots`):
+// out[(n*kMaxCon + c)*kBlock] with `out` pointing at this lane's column.
+template <int N>
+__device__ __forceinline__ void contact_rows_legleg(const EnvShared &es, const S6 cd[3], const V3 ba[3], const V3 bo[3], const float (&vb)[N][6],
+                                                    const float (&vl)[N][3], float esgn, bool et2, unsigned qm, int part_all, int slots, int slots_w,
+                                                    float *out) {
+  S6 W1[N];
+  link2_velocity<N>(cd, ba, bo, vb, vl, W1);
+#pragma unroll 1
+  for (int rem = slots_w; rem; rem &= rem - 1) {
+    const int c = __ffs(rem) - 1;
     const ContactSlot &s = es.con[c];
     const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-    const int pc = (part_all >> (4 * c)) & 15;  // 0 for c >= ncon
+    const bool mine = (slots >> c) & 1;
+    const int pc = mine ? (part_all >> (4 * c)) & 15 : 0;
     const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
-    V3 pv[N];
-#pragma unroll
-    for (int n = 0; n < N; n++) {
-      S6 W = fma6(dep == 2 ? vl[n][2] : 0.f, cd[2], W1[n]);
-      pv[n] = W.l + cross(W.a, r);  // velocity of the contact point as carried by this leg's touching link
-    }
-    float rs;  // sign of the row (folded into the result: the row is linear in pv)
-    if (ss_w || !PUPPER_ROWS_BCAST) {  // some env of the warp has a leg-leg contact: two legs may contribute, sum over the quad
-      const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
-#pragma unroll
-      for (int n = 0; n < N; n++) pv[n] = qsum3(V3{sg * pv[n].x, sg * pv[n].y, sg * pv[n].z}, qm);
-      rs = 1.f;
-    } else {  // world-vs-leg contacts only: exactly one leg touches, take its value
-      const int c1 = s.code1, c2 = s.code2;
-      const int src = qbase + ((((c2 >= 0) ? c2 : c1) >> 2) & 3);
-      rs = c < ncon ? (c2 >= 0 ? 1.f : -1.f) : 0.f;
-#pragma unroll
-      for (int n = 0; n < N; n++) pv[n] = V3{__shfl_sync(qm, pv[n].x, src), __shfl_sync(qm, pv[n].y, src), __shfl_sync(qm, pv[n].z, src)};
-    }
+    const float sg = (d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f);  // + as body2, - as body1, 0 if this leg is not involved
     const float t0 = et2 ? s.frame[6] : s.frame[3], t1 = et2 ? s.frame[7] : s.frame[4], t2 = et2 ? s.frame[8] : s.frame[5];
     const float em = esgn * s.mu;
 #pragma unroll
     for (int n = 0; n < N; n++) {
-      float jn = s.frame[0] * pv[n].x + s.frame[1] * pv[n].y + s.frame[2] * pv[n].z;
-      float jt = t0 * pv[n].x + t1 * pv[n].y + t2 * pv[n].z;
-      out[(n * kMaxCon + c) * kBlock] = rs * fmaf(em, jt, jn);
+      const S6 W = fma6(dep == 2 ? vl[n][2] : 0.f, cd[2], W1[n]);
+      V3 pv = W.l + cross(W.a, r);
+      pv = qsum3(V3{sg * pv.x, sg * pv.y, sg * pv.z}, qm);
+      const float jn = s.frame[0] * pv.x + s.frame[1] * pv.y + s.frame[2] * pv.z;
+      const float jt = t0 * pv.x + t1 * pv.y + t2 * pv.z;
+      if (mine) out[(n * kMaxCon + c) * kBlock] = fmaf(em, jt, jn);
     }
   }
 }
@@ -809,6 +858,12 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   // ---- collision (A.5): keep only contacts that can act (dist < 0), at most max_contact_points ------
   __syncwarp(qm);  // sphere centres visible to the quad
   int ncon = 0;
+  int n_ss = 0, css = 0;  // leg-leg contacts of this env: count and slot of the (last) one
+  int ss_mask = 0;        // slots of this env that hold a leg-leg contact
+  float knee_hits = 0.f, torso_hits = 0.f;
+  int own_list = 0, own_count = 0;  // world-vs-leg contacts in which this lane's leg takes part (3 bits per entry)
+  int part_all = 0;                 // participation code of this lane in every contact (4 bits per contact)
+  bool plane_only = false;          // warp-uniform: the lists above were filled by the collision fast path
   {
     float cdist[4];
     V3 cpos[4], cn[4];
@@ -927,33 +982,68 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     }
     // final cut: the max_contact_points smallest dist over [plane 0..7, box 8..11, sphere-sphere 12..15]
     const int maxc = m.max_contact_points;
-    for (int r = 0; r < maxc; r++) {
-      // local best of this lane's 4 candidates (ids grow with i, so the first minimum is also the lowest id)
-      const float bk = fminf(fminf(cdist[0], cdist[1]), fminf(cdist[2], cdist[3]));
-      const int bl = cdist[0] == bk ? 0 : (cdist[1] == bk ? 1 : (cdist[2] == bk ? 2 : 3));
-      const int bi = bk < kInf ? (bl < 2 ? 2 * k + bl : (bl == 2 ? 8 + k : 12 + k)) : 0x7fffffff;
-      float mk = bk;
-      int mi = bi;
+    const bool a0 = cdist[0] < kInf, a1 = cdist[1] < kInf, a2 = cdist[2] < kInf, a3 = cdist[3] < kInf;
+    const unsigned q0 = (__ballot_sync(qm, a0) >> qbase) & 15u, q1b = (__ballot_sync(qm, a1) >> qbase) & 15u;
+    const unsigned q2 = (__ballot_sync(qm, a2) >> qbase) & 15u, q3 = (__ballot_sync(qm, a3) >> qbase) & 15u;
+    const int nplane = __popc(q0) + __popc(q1b), total = nplane + __popc(q2) + __popc(q3);
+    if (__all_sync(qm, total <= maxc)) {
+      // Usual case: no env of the warp has more penetrating candidates than slots, so every one is kept and no ranking
+      // is needed.  Slots are handed out in candidate order (the SET of contacts is what the solver sees; the order only
+      // moves float32 rounding of sums over contacts).
+      const unsigned below = (1u << k) - 1u;
+      const int s0 = __popc(q0 & below) + __popc(q1b & below), s1 = s0 + (a0 ? 1 : 0);
+      const int s2 = nplane + __popc(q2 & below), s3 = nplane + __popc(q2) + __popc(q3 & below);
 #pragma unroll
-      for (int s = 1; s <= 2; s <<= 1) {
-        float ok = __shfl_xor_sync(qm, mk, s);
-        int oi = __shfl_xor_sync(qm, mi, s);
-        const bool take = (ok < mk) | ((ok == mk) & (oi < mi));
-        mk = take ? ok : mk; mi = take ? oi : mi;
+      for (int i = 0; i < 4; i++) {
+        const bool on = i == 0 ? a0 : (i == 1 ? a1 : (i == 2 ? a2 : a3));
+        const int slot = i == 0 ? s0 : (i == 1 ? s1 : (i == 2 ? s2 : s3));
+        if (on) {
+          ContactSlot &s = es.con[slot];
+          s.r[0] = cpos[i].x - C.x; s.r[1] = cpos[i].y - C.y; s.r[2] = cpos[i].z - C.z;
+          s.frame[0] = cn[i].x; s.frame[1] = cn[i].y; s.frame[2] = cn[i].z;
+          s.dist = cdist[i];
+          s.code1 = ccode1[i]; s.code2 = ccode2[i]; s.s1 = cs1[i]; s.s2 = cs2[i]; s.ty = ctype[i]; s.box = cbox;
+        }
       }
-      if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
-      if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish the raw candidate in slot r
-        ContactSlot &s = es.con[r];
-        V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
-        int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
+      ncon = total;
+      if (!__any_sync(qm, a2 | a3)) {  // plane contacts only: each lane knows its own contacts without looking at the slots
+        plane_only = true;
+        own_count = (a0 ? 1 : 0) + (a1 ? 1 : 0);
+        own_list = a0 ? (s0 | (a1 ? s1 << 3 : 0)) : (a1 ? s1 : 0);
+        part_all = (a0 ? 4 << (4 * s0) : 0) | (a1 ? 8 << (4 * s1) : 0);  // body2 at depth 1 (knee sphere) / depth 2 (foot sphere)
+        const float kh = (a0 ? (float)((sh.c.knee_sphere_mask >> (2 * k)) & 1u) : 0.f) + (a1 ? (float)((sh.c.knee_sphere_mask >> (2 * k + 1)) & 1u) : 0.f);
+        const float th = (a0 ? (float)((sh.c.torso_sphere_mask >> (2 * k)) & 1u) : 0.f) + (a1 ? (float)((sh.c.torso_sphere_mask >> (2 * k + 1)) & 1u) : 0.f);
+        knee_hits = qsum(kh, qm); torso_hits = qsum(th, qm);
+      }
+    } else {
+      for (int r = 0; r < maxc; r++) {
+        // local best of this lane's 4 candidates (ids grow with i, so the first minimum is also the lowest id)
+        const float bk = fminf(fminf(cdist[0], cdist[1]), fminf(cdist[2], cdist[3]));
+        const int bl = cdist[0] == bk ? 0 : (cdist[1] == bk ? 1 : (cdist[2] == bk ? 2 : 3));
+        const int bi = bk < kInf ? (bl < 2 ? 2 * k + bl : (bl == 2 ? 8 + k : 12 + k)) : 0x7fffffff;
+        float mk = bk;
+        int mi = bi;
 #pragma unroll
-        for (int i = 0; i < 4; i++) if (i == bl) { pp = cpos[i]; nn = cn[i]; c1 = ccode1[i]; c2 = ccode2[i]; s1 = cs1[i]; s2 = cs2[i]; ty = ctype[i]; cdist[i] = kInf; }
-        s.r[0] = pp.x - C.x; s.r[1] = pp.y - C.y; s.r[2] = pp.z - C.z;
-        s.frame[0] = nn.x; s.frame[1] = nn.y; s.frame[2] = nn.z;
-        s.dist = bk;
-        s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2; s.ty = ty; s.box = cbox;
+        for (int s = 1; s <= 2; s <<= 1) {
+          float ok = __shfl_xor_sync(qm, mk, s);
+          int oi = __shfl_xor_sync(qm, mi, s);
+          const bool take = (ok < mk) | ((ok == mk) & (oi < mi));
+          mk = take ? ok : mk; mi = take ? oi : mi;
+        }
+        if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
+        if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish the raw candidate in slot r
+          ContactSlot &s = es.con[r];
+          V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
+          int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) if (i == bl) { pp = cpos[i]; nn = cn[i]; c1 = ccode1[i]; c2 = ccode2[i]; s1 = cs1[i]; s2 = cs2[i]; ty = ctype[i]; cdist[i] = kInf; }
+          s.r[0] = pp.x - C.x; s.r[1] = pp.y - C.y; s.r[2] = pp.z - C.z;
+          s.frame[0] = nn.x; s.frame[1] = nn.y; s.frame[2] = nn.z;
+          s.dist = bk;
+          s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2; s.ty = ty; s.box = cbox;
+        }
+        if (mk < 0.f) ncon = r + 1;
       }
-      if (mk < 0.f) ncon = r + 1;
     }
   }
   __syncwarp(qm);  // raw contact slots visible to the quad
@@ -988,33 +1078,33 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     }
   }
   __syncwarp(qm);  // completed contact slots visible to the quad
-  int n_ss = 0, css = 0;  // leg-leg contacts of this env: count and slot of the (last) one
-  float knee_hits = 0.f, torso_hits = 0.f;
-  int own_list = 0, own_count = 0;  // world-vs-leg contacts in which this lane's leg takes part (3 bits per entry)
-  int part_all = 0;                 // participation code of this lane in every contact (4 bits per contact)
+  if (!plane_only) {
 #pragma unroll 1
-  for (int c = 0; c < ncon; c++) {
-    const ContactSlot &s = es.con[c];
-    const bool is_ss = (s.code1 >= 0 && s.code2 >= 0);
-    if (is_ss) { n_ss++; css = c; }
-    {
-      const int pc = participation(s, k);
-      part_all |= pc << (4 * c);
-      if (pc && !is_ss) { own_list |= c << (3 * own_count); own_count++; }
+    for (int c = 0; c < ncon; c++) {
+      const ContactSlot &s = es.con[c];
+      const bool is_ss = (s.code1 >= 0 && s.code2 >= 0);
+      if (is_ss) { n_ss++; css = c; ss_mask |= 1 << c; }
+      {
+        const int pc = participation(s, k);
+        part_all |= pc << (4 * c);
+        if (pc && !is_ss) { own_list |= c << (3 * own_count); own_count++; }
+      }
+      if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
+      if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
     }
-    if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
-    if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
   }
 
   // A leg-leg contact couples two legs, so its rows do not fit the arrow structure.  One such contact (the common
   // rare case) is applied to the arrow solve as a rank-<=4 update (Woodbury, below); two or more go the dense way.
   const bool one_ss = n_ss == 1, dense_env = n_ss >= 2;
-  const bool ss_w = __any_sync(qm, n_ss > 0);
+  const int ss_mask_w = plane_only ? 0 : (int)__reduce_or_sync(qm, (unsigned)ss_mask);  // slots holding a leg-leg contact somewhere in the warp
+  const int nown_w = __reduce_max_sync(qm, own_count);  // most world-vs-leg contacts on one leg, over the warp
   if (want_stale && k == 0) { es.st_hits[0] = knee_hits; es.st_hits[1] = torso_hits; }
   PHASE_SYNC();
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
   // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
   float *rowA = rows + threadIdx.x, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
+  float *rowQ = rows + (threadIdx.x & ~3);  // the same buffers seen from lane 0 of the quad: edge e of contact c at rowQ[c*kBlock + e]
   const float esgn = (k & 1) ? -1.f : 1.f;  // pyramid edge of this lane: Jn + esgn*mu*Jt[k>>1]
   const bool et2 = (k >> 1) != 0;
   float fl[3], rff[3], fD[3], fA[3];   // friction-loss rows: loss, R*loss, D, aref
@@ -1051,18 +1141,22 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   // cost at the warm start and at qacc_smooth.  (M qacc_smooth is taken as qfrc_smooth.)
   float Maw_b[6], Maw_l[3];
   tree_matvec(M, L.wb, L.wl, Maw_b, Maw_l, qm);
+  float cw_con = 0.f, cs_con = 0.f;  // constraint cost of this lane's contact rows at the warm start / at qacc_smooth
   {
     float v3b[3][6], v3l[3][3];
 #pragma unroll
     for (int d = 0; d < 6; d++) { v3b[0][d] = L.vb[d]; v3b[1][d] = L.wb[d]; v3b[2][d] = sb[d]; }
 #pragma unroll
     for (int j = 0; j < 3; j++) { v3l[0][j] = L.vl[j]; v3l[1][j] = L.wl[j]; v3l[2][j] = sl[j]; }
-    contact_rows<3>(es, ncon, k, cd, ba, bo, v3b, v3l, esgn, et2, qm, qbase, ncon_w, part_all, ss_w, rowA);
+    // contact rows at qvel / warm start / qacc_smooth, their reference accelerations and both start costs: world-vs-leg
+    // contacts by the touching leg's lane (all four edges), leg-leg contacts edge by edge with a sum over the quad
+    contact_rows_own<3, true>(es, cd, ba, bo, v3b, v3l, own_list, own_count, nown_w, part_all, rowQ, cw_con, cs_con);
+    if (ss_mask_w) contact_rows_legleg<3>(es, cd, ba, bo, v3b, v3l, esgn, et2, qm, part_all, ss_mask, ss_mask_w, rowA);
   }
   float cost_w, cost_s, gauss_w;
   float jaw_f[3], jaw_l[3], jas_f[3], jas_l[3];
   {
-    float cw = 0.f, cs = 0.f;
+    float cw = cw_con, cs = cs_con;
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       // friction-loss row (Huber): 0.5 D x^2 inside |x| < R f, f (|x| - R f / 2) outside; a row without friction loss
@@ -1082,16 +1176,20 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         cs = fmaf(0.5f * lD[j] * ms, ms, cs);
       }
     }
+    if (ss_mask_w) {  // leg-leg slots hold raw rows: turn this lane's edge into Jaref and add its cost
 #pragma unroll 1
-    for (int c = 0; c < ncon; c++) {
-      const ContactSlot &s = es.con[c];
-      float aref = -s.b * rowA[c * kBlock] - s.kimp;
-      float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
-      rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;   // now Jaref at the warm start / at qacc_smooth
-      const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
-      cw = fmaf(0.5f * s.D * mw, mw, cw);
-      cs = fmaf(0.5f * s.D * ms, ms, cs);
+      for (int rem = ss_mask; rem; rem &= rem - 1) {
+        const int c = __ffs(rem) - 1;
+        const ContactSlot &s = es.con[c];
+        float aref = -s.b * rowA[c * kBlock] - s.kimp;
+        float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
+        rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;
+        const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
+        cw = fmaf(0.5f * s.D * mw, mw, cw);
+        cs = fmaf(0.5f * s.D * ms, ms, cs);
+      }
     }
+    __syncwarp(qm);  // Jaref rows written by the owning lanes are visible to every edge's lane
     float gw = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) gw = fmaf(Maw_l[j] - fs_l[j], L.wl[j] - sl[j], gw);
@@ -1151,53 +1249,33 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       }
     }
     S6 S1 = S6{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, S2 = S1, Sb = S1;  // wrenches on link2 / link3 chains, base
+    // World-vs-leg contacts, each handled by the lane whose leg touches (it has the chain's cdofs): the four pyramid-edge
+    // forces -> contact-frame force -> world wrench about C on this leg's chain and on the base, and the Hessian block
+    // Jc^T W Jc with the 3x3 contact-frame weight W of the active edges.  The 4 lanes of a quad work on different contacts
+    // at the same time; the trip count is the warp-wide maximum of contacts per leg (typically 1-2).
 #pragma unroll 1
-    for (int c = 0; c < ncon_w; c++) {
-      const ContactSlot &s = es.con[c];
-      const bool con_on = c < ncon;
-      const float ja = con_on ? rowJ[c * kBlock] : 0.f;
-      float act = ja < 0.f ? 1.f : 0.f;
-      float fe = -s.D * ja * act;  // force of this lane's pyramid edge
-      float de = s.D * act;
-      float f0 = __shfl_sync(qm, fe, qbase + 0), f1 = __shfl_sync(qm, fe, qbase + 1), f2 = __shfl_sync(qm, fe, qbase + 2), f3 = __shfl_sync(qm, fe, qbase + 3);
-      float d0 = __shfl_sync(qm, de, qbase + 0), d1 = __shfl_sync(qm, de, qbase + 1), d2 = __shfl_sync(qm, de, qbase + 2), d3 = __shfl_sync(qm, de, qbase + 3);
-      // contact-frame force and world wrench about C
-      float Fn = (f0 + f1) + (f2 + f3), Ft1 = s.mu * (f0 - f1), Ft2 = s.mu * (f2 - f3);
-      V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
-                s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
-      V3 r = V3{s.r[0], s.r[1], s.r[2]};
-      S6 w = S6{cross(r, g), g};
-      const int pc = (part_all >> (4 * c)) & 15;  // 0 for c >= ncon
-      int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
-      float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
-      S1 = fma6(s1w, w, S1);
-      S2 = fma6(s2w, w, S2);
-      float wb_ = con_on ? (s.code2 >= 0 ? 1.f : 0.f) - (s.code1 >= 0 ? 1.f : 0.f) : 0.f;
-      Sb = fma6(wb_, w, Sb);
-      // weights of the 3x3 contact-frame Hessian block W (from the 4 pyramid-edge weights), kept for the build below
-      if (k == 0 && con_on) {
-        float *wv = es.conW[c];
-        wv[0] = (d0 + d1) + (d2 + d3); wv[1] = s.mu * (d0 - d1); wv[2] = s.mu * (d2 - d3);
-        wv[3] = s.mu * s.mu * (d0 + d1); wv[4] = s.mu * s.mu * (d2 + d3);
-      }
-    }
-    // Hessian: H += Jc^T W Jc for world-vs-leg contacts.  Each lane walks ITS OWN contacts (the leg that touches
-    // has the cdofs), so the 4 lanes of a quad build different contacts at the same time; the trip count is the
-    // warp-wide maximum of contacts per leg (typically 1-2), not the number of contacts of the env.
-    __syncwarp(qm);
-    if (!__all_sync(qm, dense_env)) {
-      const int nown_w = __reduce_max_sync(qm, dense_env ? 0 : own_count);
-#pragma unroll 1
-      for (int i = 0; i < nown_w; i++) {
+    for (int i = 0; i < nown_w; i++) {
+      if (i < own_count) {
         const int c = (own_list >> (3 * i)) & 7;
         const ContactSlot &s = es.con[c];
-        const float *wv = es.conW[c];
-        const float W00 = wv[0];
-        if (i < own_count && !dense_env && W00 > 0.f) {
-          const float W01 = wv[1], W02 = wv[2], W11 = wv[3], W22 = wv[4];
-          const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-          const int pc = (part_all >> (4 * c)) & 15;
-          const int dep = (pc & 3) | ((pc >> 2) & 3);
+        const float *ja = rowJ - k + c * kBlock;  // the four edges' Jaref
+        const float D = s.D, mu = s.mu;
+        const float j0 = ja[0], j1 = ja[1], j2 = ja[2], j3 = ja[3];
+        const float d0 = j0 < 0.f ? D : 0.f, d1 = j1 < 0.f ? D : 0.f, d2 = j2 < 0.f ? D : 0.f, d3 = j3 < 0.f ? D : 0.f;
+        const float f0 = -d0 * j0, f1 = -d1 * j1, f2 = -d2 * j2, f3 = -d3 * j3;
+        const float Fn = (f0 + f1) + (f2 + f3), Ft1 = mu * (f0 - f1), Ft2 = mu * (f2 - f3);
+        const V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
+                        s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
+        const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+        const int pc = (part_all >> (4 * c)) & 15;
+        const int dep = (pc & 3) | ((pc >> 2) & 3);
+        const float sg = (pc >> 2) ? 1.f : -1.f;  // + as body2, - as body1
+        const S6 w = S6{sg * cross(r, g), sg * g};
+        if (dep == 1) S1 = S1 + w; else S2 = S2 + w;
+        Sb = Sb + w;
+        const float W00 = (d0 + d1) + (d2 + d3);
+        if (!dense_env && W00 > 0.f) {
+          const float W01 = mu * (d0 - d1), W02 = mu * (d2 - d3), W11 = mu * mu * (d0 + d1), W22 = mu * mu * (d2 + d3);
           float Jc[9][3], T[9][3];
 #pragma unroll
           for (int d = 0; d < 9; d++) {
@@ -1224,6 +1302,29 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
           }
         }
+      }
+    }
+    Sb = qsum6(Sb, qm);  // the base carries every world-vs-leg contact
+    if (ss_mask_w) {
+      // Leg-leg contacts: equal and opposite wrenches on the two legs' chains, nothing on the base (its columns cancel).
+      // Their Hessian rows couple two legs: Woodbury / dense paths below.
+#pragma unroll 1
+      for (int rem = ss_mask; rem; rem &= rem - 1) {
+        const int c = __ffs(rem) - 1;
+        const ContactSlot &s = es.con[c];
+        const float *ja = rowJ - k + c * kBlock;
+        const float D = s.D, mu = s.mu;
+        const float f0 = -D * fminf(ja[0], 0.f), f1 = -D * fminf(ja[1], 0.f), f2 = -D * fminf(ja[2], 0.f), f3 = -D * fminf(ja[3], 0.f);
+        const float Fn = (f0 + f1) + (f2 + f3), Ft1 = mu * (f0 - f1), Ft2 = mu * (f2 - f3);
+        const V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
+                        s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
+        const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+        const S6 w = S6{cross(r, g), g};
+        const int pc = (part_all >> (4 * c)) & 15;
+        const int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
+        const float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
+        S1 = fma6(s1w, w, S1);
+        S2 = fma6(s2w, w, S2);
       }
     }
     // qfrc_constraint and gradient
@@ -1358,7 +1459,10 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       for (int d = 0; d < 6; d++) v1b[0][d] = hb[d];
 #pragma unroll
       for (int j = 0; j < 3; j++) v1l[0][j] = hl[j];
-      contact_rows<1>(es, ncon, k, cd, ba, bo, v1b, v1l, esgn, et2, qm, qbase, ncon_w, part_all, ss_w, rowA);  // jv of the contact-edge rows
+      float unused0 = 0.f, unused1 = 0.f;
+      contact_rows_own<1, false>(es, cd, ba, bo, v1b, v1l, own_list, own_count, nown_w, part_all, rowQ, unused0, unused1);  // jv of the contact-edge rows
+      if (ss_mask_w) contact_rows_legleg<1>(es, cd, ba, bo, v1b, v1l, esgn, et2, qm, part_all, ss_mask, ss_mask_w, rowA);
+      __syncwarp(qm);
     }
     float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];
     float q1l = 0.f, q2l = 0.f;

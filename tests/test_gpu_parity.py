@@ -204,7 +204,7 @@ def test_leg_leg_contacts_take_the_dense_path():
     legs in the Hessian: one such contact is a low-rank (Woodbury) update of the arrow solve, two or more take the
     dense fallback of the Newton direction.  Both groups are checked."""
     env = common.make_env(environment_timestep=0.004, **QUIET)
-    n = 512
+    n = 2048  # ~10 % of the envs get one leg-leg contact, ~1 % two or more: enough members for group quantiles
     h, O, O32 = _pair(env, n, debug=True)
     keys = common.env_keys(n)
     O.reset(keys); h.reset(keys)
