@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PUPPER_ABI_VERSION 1
+#define PUPPER_ABI_VERSION 2
 
 /* Fixed topology of the supported robot family: world + base + 4 legs x 3 links. */
 #define PUPPER_NBODY 14
@@ -41,8 +41,13 @@ extern "C" {
 #define PUPPER_NSPHERE 8 /* per leg: link2 "knee" sphere, link3 "foot" sphere */
 #define PUPPER_NSITE 5
 #define PUPPER_MAX_BOX 32
-#define PUPPER_MAX_CON 8   /* upper bound for the model's max_contact_points */
-#define PUPPER_MAX_PAIRS 8 /* upper bound for the model's max_geom_pairs */
+#define PUPPER_MAX_CON 8   /* storage bound of contact tables (the CPU oracle's taps use it) */
+#define PUPPER_MAX_PAIRS 8 /* storage bound of per-group pair tables */
+#define PUPPER_KERNEL_MAX_CON 5   /* what the CUDA path accepts: 1 <= max_contact_points <= 5 (one slot table per env) */
+#define PUPPER_KERNEL_MAX_PAIRS 4 /* and 1 <= max_geom_pairs <= 4 (one narrow phase per lane of the env's quad); the
+                                     reference model sets 5 / 4 (test_pupper_model.xml:227-230); MJX's -1 = "no limit" is
+                                     outside the supported family (pupper_model_create: PUPPER_EUNSUPPORTED) */
+#define PUPPER_NRAND 44    /* uniform draws one reset / step consumes per env (PupperRand) */
 #define PUPPER_MAX_LAT 8   /* longest latency distribution (action and IMU) */
 #define PUPPER_NREWARD 18
 #define PUPPER_NMETRIC 19 /* total_dist + 18 scaled reward terms */
@@ -235,7 +240,32 @@ typedef struct PupperStepOut {
   int32_t *dbg_contact_geom;/* [n_envs][max_contact_points][2] */
   float *dbg_site_xpos;  /* [n_envs][5][3] */
   float *dbg_qacc;       /* [n_envs][18] */
+  /* solver decisions of the last substep (oracle: OracleDebug.used_warmstart / ls_iters / ls_alpha / efc_zone0):
+   *   [0] 1 if the Newton iteration started from qacc_warmstart, 0 if from qacc_smooth
+   *   [1] bracket refinements of the line search this env ran (MJX's loop counter, 0..ls_iterations)
+   *   [2] number of active contacts (dist < 0, after the max_contact_points cut)
+   *   [3] zone of the 12 friction-loss rows at the start point, 2 bits per hinge dof (1 quadratic, 2 / 3 linear -/+)
+   *   [4] bit j: limit row of hinge j active at the start point
+   *   [5] bit 4c+e: pyramid edge e of contact slot c active at the start point (slots as in dbg_contact_*)
+   *   [6] the accepted step size alpha (float bits)
+   *   [7] number of leg-leg contacts among [2] */
+  int32_t *dbg_solver;   /* [n_envs][8] */
 } PupperStepOut;
+
+/* External randoms (optional; NULL = every draw is made in-kernel with threefry2x32 from state->rng).
+ * u holds RAW uniforms in [0, 1) -- what jax.random.uniform produces before its affine map -- one row per draw; the
+ * kernel applies the reference's ranges / thresholds to them (max(lo, u*(hi-lo)+lo), choice via searchsorted).  With
+ * external randoms state->rng is neither read nor written, so physics / reward / observation parity can be checked
+ * without relying on the restated key tree (draw sites: environment.py:349-361, 499-523, 256-269, 291-293).
+ * Rows for pupper_step:  0 kick x, 1 kick y, 2 kick Bernoulli, 3 action-latency choice, 4-6 angular-velocity noise,
+ *   7-9 gravity noise, 10-21 motor-angle noise, 22-33 last-action noise, 34 IMU-latency choice, 35-37 command
+ *   (lin x, lin y, yaw), 38 zero-command Bernoulli, 39-41 near-zero command, 42 pitch, 43 roll (35-43 are used only in
+ *   a step that resamples the command).
+ * Rows for pupper_reset: 0-2 start position x, y, z, 3 start yaw; 4-43 as above. */
+typedef struct PupperRand {
+  int32_t stride;
+  const float *u; /* [PUPPER_NRAND][stride] device */
+} PupperRand;
 
 /* Fused brax EpisodeWrapper + AutoResetWrapper, device SoA, optional. */
 typedef struct PupperEpisode {
@@ -250,7 +280,8 @@ typedef struct PupperEpisode {
   float *length;          /* [stride] */
   float *sum_metrics;     /* [19][stride] */
   float *episode_done;    /* [stride] previous step's done */
-  float *totals;          /* [24] device accumulator: completed-episode sums, all-reduced across ranks */
+  float *totals;          /* [24] device accumulator of COMPLETED episodes, all-reduced across ranks: [0] episodes, [1] sum_reward,
+                             [2] length, [3..21] the 19 metric sums, [22] terminations (done without truncation), [23] reserved (0) */
 } PupperEpisode;
 
 typedef struct PupperModel PupperModel; /* opaque: device-resident constant tables */
@@ -267,20 +298,20 @@ int pupper_model_destroy(PupperModel *model);
 /* keys: device uint32 [n_envs][2] (one JAX PRNG key per env, as vmap(reset) receives them). */
 int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, const PupperDR *dr,
                  PupperState *state, PupperStepOut *out, PupperEpisode *episode,
-                 pupper_stream_t stream);
+                 const PupperRand *ext_rand, pupper_stream_t stream);
 
 /* action: device float32 [n_envs][12] row-major (as jax.vmap(env.step) receives it).  Every random
  * draw of the step (kick, latency picks, observation noise, command resampling) is made in-kernel
  * with threefry2x32 from state->rng exactly as the reference's key tree.
  * episode != NULL fuses brax EpisodeWrapper + AutoResetWrapper after the env step. */
 int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, PupperState *state,
-                const float *action, PupperStepOut *out, PupperEpisode *episode,
-                pupper_stream_t stream);
+                const float *action, const PupperRand *ext_rand, PupperStepOut *out,
+                PupperEpisode *episode, pupper_stream_t stream);
 
 /* Measurement helper (bench.py): enqueues an FP32 FMA probe of blocks*256*iters*16 flop, to time with CUDA
  * events for the measured FP32 roofline denominator. device_sink: any device float (never written). */
 int pupper_probe_ffma(int blocks, int iters, float *device_sink, pupper_stream_t stream);
-int pupper_sizeof(int which); /* 0..5: sizeof PupperModelDesc, EnvCfg, State, DR, StepOut, Episode (binding self-check) */
+int pupper_sizeof(int which); /* 0..6: sizeof PupperModelDesc, EnvCfg, State, DR, StepOut, Episode, Rand (binding self-check) */
 
 /* Number of kernels the last pupper_step / pupper_reset call on this model enqueued. */
 int pupper_last_launch_count(const PupperModel *model);

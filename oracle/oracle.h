@@ -86,6 +86,7 @@ typedef struct OracleDebug {
   int32_t ncon, nefc, ls_iters, used_warmstart;
   int32_t contact_flags; /* bit k: contact, bit 4+k: contact_filt_cm, bit 8+k: first_contact */
   int32_t act_lag, imu_lag, resampled;
+  int32_t efc_zone0[ORACLE_MAX_EFC]; /* row zones at the Newton start point: 0 inactive, 1 quadratic, 2 / 3 linear (-/+) */
 } OracleDebug;
 
 #ifdef __cplusplus
@@ -107,6 +108,17 @@ int oracle_reset_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, c
                      const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads);
 int oracle_step_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr,
                     OracleEnv *envs, const double *action, int episode, OracleDebug *dbg, int n_threads);
+
+/* Same with external randoms: ext_u = NULL, or host float [n][PUPPER_NRAND] raw uniforms in [0, 1), rows as documented
+ * for PupperRand in include/pupper_env.h; envs[i].rng is then left unchanged. */
+int oracle_reset_ext_f64(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const uint32_t *keys,
+                         const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads, const float *ext_u);
+int oracle_step_ext_f64(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr,
+                        OracleEnv *envs, const double *action, int episode, OracleDebug *dbg, int n_threads, const float *ext_u);
+int oracle_reset_ext_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const uint32_t *keys,
+                         const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads, const float *ext_u);
+int oracle_step_ext_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr,
+                        OracleEnv *envs, const double *action, int episode, OracleDebug *dbg, int n_threads, const float *ext_u);
 
 /* PRNG known-answer access (jax 0.5.0 threefry, partitionable). */
 void oracle_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t *out);

@@ -53,8 +53,9 @@ DEBUG_DTYPE = np.dtype([
     ("rewards_raw", f8, NREWARD), ("motor_targets", f8, NU),
     ("contact_geom", np.int32, (MAX_CON, 2)), ("ncon", np.int32), ("nefc", np.int32), ("ls_iters", np.int32),
     ("used_warmstart", np.int32), ("contact_flags", np.int32), ("act_lag", np.int32), ("imu_lag", np.int32),
-    ("resampled", np.int32),
+    ("resampled", np.int32), ("efc_zone0", np.int32, MAX_EFC),
 ], align=True)
+NRAND = 44  # rows of the external-randoms table (include/pupper_env.h PupperRand)
 
 
 def build(force: bool = False) -> str:
@@ -113,25 +114,34 @@ class Oracle:
         """dr: structured array of DR_DTYPE (one row per env) or None."""
         self.dr = None if dr is None else np.ascontiguousarray(dr, dtype=DR_DTYPE)
 
-    def reset(self, keys: np.ndarray, debug: bool = False) -> np.ndarray:
+    @staticmethod
+    def _ext(ext_rand: Optional[np.ndarray], n: int) -> Optional[np.ndarray]:
+        """External randoms [n, 44] float32 in [0, 1) (env-major here; the device table of the CUDA path is [44, n])."""
+        if ext_rand is None:
+            return None
+        ext = np.ascontiguousarray(ext_rand, dtype=np.float32)
+        assert ext.shape == (n, NRAND), ext.shape
+        return ext
+
+    def reset(self, keys: np.ndarray, debug: bool = False, ext_rand: Optional[np.ndarray] = None) -> np.ndarray:
         keys = np.ascontiguousarray(keys, dtype=np.uint32).reshape(-1, 2)
         n = keys.shape[0]
         self.envs = np.zeros(n, dtype=ENV_DTYPE)
         self.debug = np.zeros(n, dtype=DEBUG_DTYPE) if debug else None
-        fn = getattr(self.l, f"oracle_reset_{self.suffix}")
+        fn = getattr(self.l, f"oracle_reset_ext_{self.suffix}")
         rc = fn(C.byref(self.model), C.byref(self.cfg), n, _ptr(keys), _ptr(self.dr), _ptr(self.envs),
-                _ptr(self.debug), self.n_threads)
+                _ptr(self.debug), self.n_threads, _ptr(self._ext(ext_rand, n)))
         assert rc == 0, rc
         return self.envs
 
-    def step(self, action: np.ndarray, episode: bool = False, debug: bool = False) -> np.ndarray:
+    def step(self, action: np.ndarray, episode: bool = False, debug: bool = False, ext_rand: Optional[np.ndarray] = None) -> np.ndarray:
         n = self.envs.shape[0]
         action = np.ascontiguousarray(action, dtype=np.float64).reshape(n, NU)
         if debug and self.debug is None:
             self.debug = np.zeros(n, dtype=DEBUG_DTYPE)
-        fn = getattr(self.l, f"oracle_step_{self.suffix}")
+        fn = getattr(self.l, f"oracle_step_ext_{self.suffix}")
         rc = fn(C.byref(self.model), C.byref(self.cfg), n, _ptr(self.dr), _ptr(self.envs), _ptr(action),
-                int(episode), _ptr(self.debug) if debug else None, self.n_threads)
+                int(episode), _ptr(self.debug) if debug else None, self.n_threads, _ptr(self._ext(ext_rand, n)))
         assert rc == 0, rc
         return self.envs
 

@@ -117,6 +117,30 @@ static inline void split_key(const uint32_t key[2], uint32_t i, uint32_t out[2])
   oracle_threefry2x32(key[0], key[1], 0u, i, out);
 }
 
+/* External randoms (include/pupper_env.h PupperRand): when set, every draw of the env step / reset takes the raw
+ * [0, 1) uniform of its row from this env's table instead of threefry, and gets jax.random.uniform's affine map. */
+static __thread const float *g_ext = NULL;
+static float du(int row, const uint32_t key[2], uint32_t index, float lo, float hi) {
+  if (!g_ext) return oracle_uniform(key[0], key[1], index, lo, hi);
+  float f = g_ext[row];
+  volatile float scale = hi - lo;
+  volatile float prod = f * scale;
+  float v = prod + lo;
+  return v > lo ? v : lo;
+}
+static int dchoice(int row, const uint32_t key[2], const float *p, int n) {
+  if (!g_ext) return oracle_choice(key[0], key[1], p, n);
+  float cum[PUPPER_MAX_LAT];
+  volatile float acc = 0.0f;
+  for (int i = 0; i < n; i++) { acc = acc + p[i]; cum[i] = acc; }
+  float u = du(row, key, 0u, 0.0f, 1.0f);
+  volatile float one_minus = 1.0f - u;
+  float r = cum[n - 1] * one_minus;
+  int idx = 0;
+  for (int i = 0; i < n; i++) idx += (cum[i] < r);
+  return idx;
+}
+
 /* ------------------------------------------------------------------------------------------
  * small math (MJX math.py / brax math.py conventions)
  * ---------------------------------------------------------------------------------------- */
@@ -312,6 +336,7 @@ typedef struct {
   real qacc[NV], qfrc_constraint[NV];
   real ls_alpha, cost_start, cost_end, warm_cost, smooth_cost;
   int ls_iters, used_warmstart;
+  int zone0[MAXEFC]; /* row zones at the start point of the Newton iteration (0 inactive, 1 quadratic, 2 / 3 linear) */
 } Data;
 
 static void kinematics(const Model *M, real *qpos, Data *D) {
@@ -872,6 +897,7 @@ static void solve(const Model *M, Data *D, const real *qacc_warmstart) {
   D->used_warmstart = warm.cost < smth.cost;
   c = D->used_warmstart ? &warm : &smth;
   D->cost_start = c->cost;
+  for (int r = 0; r < D->nefc; r++) D->zone0[r] = row_zone(D, r, c->Jaref[r]);
   /* gradient, Hessian, Newton direction */
   real grad[NV], H[NV * NV], L[NV * NV], search[NV];
   for (int d = 0; d < NV; d++) grad[d] = c->Ma[d] - D->qfrc_smooth[d] - c->qfrc_constraint[d];
@@ -973,18 +999,18 @@ static void brax_x_xd(const Data *D, BraxX *X) { /* brax/mjx/pipeline.py (A.9) *
   }
 }
 
-static inline real unif(const uint32_t key[2], uint32_t i, float lo, float hi) { return (real)oracle_uniform(key[0], key[1], i, lo, hi); }
+static inline real unif(int row, const uint32_t key[2], uint32_t i, float lo, float hi) { return (real)du(row, key, i, lo, hi); }
 
 static void sample_command(const PupperEnvCfg *cfg, const uint32_t key[2], real cmd[3]) { /* environment.py:246-272 */
   uint32_t k[6][2];
   for (uint32_t i = 0; i < 6; i++) split_key(key, i, k[i]);
-  real c0 = unif(k[1], 0, cfg->lin_vel_x[0], cfg->lin_vel_x[1]);
-  real c1 = unif(k[2], 0, cfg->lin_vel_y[0], cfg->lin_vel_y[1]);
-  real c2 = unif(k[3], 0, cfg->ang_vel_yaw[0], cfg->ang_vel_yaw[1]);
-  float zp = oracle_uniform(k[4][0], k[4][1], 0, 0.0f, 1.0f);
+  real c0 = unif(35, k[1], 0, cfg->lin_vel_x[0], cfg->lin_vel_x[1]);
+  real c1 = unif(36, k[2], 0, cfg->lin_vel_y[0], cfg->lin_vel_y[1]);
+  real c2 = unif(37, k[3], 0, cfg->ang_vel_yaw[0], cfg->ang_vel_yaw[1]);
+  float zp = du(38, k[4], 0, 0.0f, 1.0f);
   float thr = cfg->stand_still_command_threshold;
   if (zp < cfg->zero_command_probability) {
-    for (uint32_t i = 0; i < 3; i++) cmd[i] = unif(k[5], i, -thr, thr);
+    for (uint32_t i = 0; i < 3; i++) cmd[i] = unif(39 + (int)i, k[5], i, -thr, thr);
   } else { cmd[0] = c0; cmd[1] = c1; cmd[2] = c2; }
 }
 
@@ -993,8 +1019,8 @@ static void sample_body_orientation(const PupperEnvCfg *cfg, const uint32_t key[
   split_key(key, 1, kp);
   split_key(key, 2, kr);
   /* float32 throughout in the reference; the f64 build keeps the f32 draws and widens the trigonometry */
-  real pitch = (real)(float)(oracle_uniform(kp[0], kp[1], 0, -1.0f, 1.0f) * cfg->maximum_pitch_command);
-  real roll = (real)(float)(oracle_uniform(kr[0], kr[1], 0, -1.0f, 1.0f) * cfg->maximum_roll_command);
+  real pitch = (real)(float)(du(42, kp, 0, -1.0f, 1.0f) * cfg->maximum_pitch_command);
+  real roll = (real)(float)(du(43, kr, 0, -1.0f, 1.0f) * cfg->maximum_roll_command);
   real v[3] = {roll, pitch, 0}, c[3], s[3];
 #ifdef ORACLE_F32
   const real pi = 3.14159274101257324f;
@@ -1009,12 +1035,12 @@ static void sample_body_orientation(const PupperEnvCfg *cfg, const uint32_t key[
 }
 
 /* utils.sample_lagged_value (utils.py:49-69): push front, categorical pick of one column */
-static int lagged(const uint32_t key[2], real *buf, int rows, int L, const real *newv, const float *p, real *out) {
+static int lagged(int row, const uint32_t key[2], real *buf, int rows, int L, const real *newv, const float *p, real *out) {
   for (int j = 0; j < rows; j++) {
     for (int l = L - 1; l > 0; l--) buf[j * L + l] = buf[j * L + l - 1];
     buf[j * L + 0] = newv[j];
   }
-  int idx = oracle_choice(key[0], key[1], p, L);
+  int idx = dchoice(row, key, p, L);
   if (idx > L - 1) idx = L - 1; /* jnp.take clips out-of-range indices */
   for (int j = 0; j < rows; j++) out[j] = buf[j * L + idx];
   return idx;
@@ -1052,22 +1078,22 @@ static void get_obs(const PupperEnvCfg *cfg, const BraxX *X, uint32_t rng[2], En
   real imu[6], down[3] = {0, 0, -1}, g[3];
   rotate(down, inv, g);
   for (uint32_t i = 0; i < 3; i++) {
-    real an = (real)(float)(oracle_uniform(k[1][0], k[1][1], i, -1.0f, 1.0f) * cfg->angular_velocity_noise);
-    real gn = (real)(float)(oracle_uniform(k[2][0], k[2][1], i, -1.0f, 1.0f) * cfg->gravity_noise);
+    real an = (real)(float)(du(4 + (int)i, k[1], i, -1.0f, 1.0f) * cfg->angular_velocity_noise);
+    real gn = (real)(float)(du(7 + (int)i, k[2], i, -1.0f, 1.0f) * cfg->gravity_noise);
     imu[i] = ang[i] + an;
     g[i] = g[i] + gn;
   }
   real gnorm = R_SQRT(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
   for (int i = 0; i < 3; i++) imu[3 + i] = g[i] / gnorm;
   real lag[6];
-  int il = lagged(k[5], r->ibuf, 6, cfg->n_imu_latency, imu, cfg->imu_latency_distribution, lag);
+  int il = lagged(34, k[5], r->ibuf, 6, cfg->n_imu_latency, imu, cfg->imu_latency_distribution, lag);
   if (dbg) dbg->imu_lag = il;
   real obs[PUPPER_OBS_DIM];
   for (int i = 0; i < 6; i++) obs[i] = lag[i];
   for (int i = 0; i < 3; i++) { obs[6 + i] = r->command[i]; obs[9 + i] = r->desired_z[i]; }
   for (uint32_t i = 0; i < 12; i++) {
-    real mn = (real)(float)(oracle_uniform(k[3][0], k[3][1], i, -1.0f, 1.0f) * cfg->motor_angle_noise);
-    real ln = (real)(float)(oracle_uniform(k[4][0], k[4][1], i, -1.0f, 1.0f) * cfg->last_action_noise);
+    real mn = (real)(float)(du(10 + (int)i, k[3], i, -1.0f, 1.0f) * cfg->motor_angle_noise);
+    real ln = (real)(float)(du(22 + (int)i, k[4], i, -1.0f, 1.0f) * cfg->last_action_noise);
     obs[12 + i] = q_joint[i] - (real)cfg->default_pose[i] + mn;
     obs[24 + i] = r->last_act[i] + ln;
   }
@@ -1096,6 +1122,7 @@ static void debug_fill(const Data *D, const BraxX *X, OracleDebug *g) {
   g->ls_alpha = (double)D->ls_alpha; g->cost_start = (double)D->cost_start; g->cost_end = (double)D->cost_end;
   g->warm_cost = (double)D->warm_cost; g->smooth_cost = (double)D->smooth_cost;
   g->ncon = D->ncon; g->nefc = D->nefc; g->ls_iters = D->ls_iters; g->used_warmstart = D->used_warmstart;
+  for (int r = 0; r < D->nefc; r++) g->efc_zone0[r] = D->zone0[r];
 }
 
 static void env_reset(const PupperModelDesc *md, const PupperEnvCfg *cfg, const uint32_t key_in[2], const OracleDR *dr,
@@ -1111,9 +1138,9 @@ static void env_reset(const PupperModelDesc *md, const PupperEnvCfg *cfg, const 
   /* randomize_qpos (domain_randomization.py:188-210) */
   for (uint32_t i = 0; i < 3; i++) split_key(k[3], i, kq[i]);
   for (int i = 0; i < NQ; i++) r.qpos[i] = (real)cfg->init_q[i];
-  for (uint32_t i = 0; i < 3; i++) r.qpos[i] = unif(kq[1], i, cfg->start_pos_min[i], cfg->start_pos_max[i]);
+  for (uint32_t i = 0; i < 3; i++) r.qpos[i] = unif((int)i, kq[1], i, cfg->start_pos_min[i], cfg->start_pos_max[i]);
   {
-    float yaw = oracle_uniform(kq[2][0], kq[2][1], 0, -3.14159274101257324f, 3.14159274101257324f);
+    float yaw = du(3, kq[2], 0, -3.14159274101257324f, 3.14159274101257324f);
     real h = (real)yaw / 2;
     r.qpos[3] = R_COS(h); r.qpos[4] = 0; r.qpos[5] = 0; r.qpos[6] = R_SIN(h);
   }
@@ -1129,7 +1156,7 @@ static void env_reset(const PupperModelDesc *md, const PupperEnvCfg *cfg, const 
   get_obs(cfg, &X, rng, &r, r.qpos + 7, dbg);
   memset(e, 0, sizeof(*e));
   env_store(e, &r);
-  e->rng[0] = rng[0]; e->rng[1] = rng[1];
+  if (!g_ext) { e->rng[0] = rng[0]; e->rng[1] = rng[1]; } else { e->rng[0] = key_in[0]; e->rng[1] = key_in[1]; }
   /* AutoResetWrapper.reset: remember the first pipeline state and obs */
   for (int i = 0; i < NQ; i++) e->first_qpos[i] = e->qpos[i];
   for (int i = 0; i < NV; i++) { e->first_qvel[i] = e->qvel[i]; e->first_warmstart[i] = e->qacc_warmstart[i]; }
@@ -1154,16 +1181,16 @@ static void env_step(const PupperModelDesc *md, const PupperEnvCfg *cfg, const O
   /* S2 kick */
   real kick[2];
   {
-    int hit = oracle_uniform(k[3][0], k[3][1], 0, 0.0f, 1.0f) < cfg->kick_probability;
+    int hit = du(2, k[3], 0, 0.0f, 1.0f) < cfg->kick_probability;
     for (uint32_t i = 0; i < 2; i++) {
-      float u = oracle_uniform(k[2][0], k[2][1], i, -1.0f, 1.0f) * cfg->kick_vel;
+      float u = du((int)i, k[2], i, -1.0f, 1.0f) * cfg->kick_vel;
       kick[i] = (real)(u * (float)hit);
       r.qvel[i] = kick[i] + r.qvel[i];
     }
   }
   /* S3 action latency, S4 motor targets */
   real lag[NU], ctrl[NU];
-  int al = lagged(k[4], r.abuf, NU, cfg->n_latency, action, cfg->latency_distribution, lag);
+  int al = lagged(3, k[4], r.abuf, NU, cfg->n_latency, action, cfg->latency_distribution, lag);
   for (int i = 0; i < NU; i++)
     ctrl[i] = r_clip((real)cfg->default_pose[i] + lag[i] * (real)cfg->action_scale, (real)cfg->joint_lower[i], (real)cfg->joint_upper[i]);
   /* S5 physics: n_frames x mjx.step */
@@ -1290,7 +1317,7 @@ static void env_step(const PupperModelDesc *md, const PupperEnvCfg *cfg, const O
   if (dbg) dbg->resampled = resample;
   /* S12 outputs */
   env_store(e, &r);
-  e->rng[0] = rng[0]; e->rng[1] = rng[1];
+  if (!g_ext) { e->rng[0] = rng[0]; e->rng[1] = rng[1]; } /* external randoms leave the key alone */
   e->last_contact = (uint32_t)contact;
   e->step = step;
   e->reward = (double)reward;
@@ -1321,24 +1348,41 @@ static void env_step(const PupperModelDesc *md, const PupperEnvCfg *cfg, const O
   }
 }
 
-int SUF(oracle_reset)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const uint32_t *keys,
-                      const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads) {
+/* ext_u: NULL, or host float [n][PUPPER_NRAND] raw uniforms in [0, 1) (rows as documented for PupperRand) */
+int SUF(oracle_reset_ext)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const uint32_t *keys,
+                          const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads, const float *ext_u) {
   if (!m || !cfg || !keys || !envs || n <= 0 || cfg->observation_history > ORACLE_MAX_HIST) return -1;
 #ifdef _OPENMP
   if (n_threads <= 0) n_threads = omp_get_max_threads();
 #pragma omp parallel for num_threads(n_threads) schedule(static)
 #endif
-  for (int i = 0; i < n; i++) env_reset(m, cfg, keys + 2 * i, dr ? dr + i : NULL, envs + i, dbg ? dbg + i : NULL);
+  for (int i = 0; i < n; i++) {
+    g_ext = ext_u ? ext_u + (size_t)PUPPER_NRAND * i : NULL;
+    env_reset(m, cfg, keys + 2 * i, dr ? dr + i : NULL, envs + i, dbg ? dbg + i : NULL);
+    g_ext = NULL;
+  }
   return 0;
 }
+int SUF(oracle_reset)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const uint32_t *keys,
+                      const OracleDR *dr, OracleEnv *envs, OracleDebug *dbg, int n_threads) {
+  return SUF(oracle_reset_ext)(m, cfg, n, keys, dr, envs, dbg, n_threads, NULL);
+}
 
-int SUF(oracle_step)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr, OracleEnv *envs,
-                     const double *action, int episode, OracleDebug *dbg, int n_threads) {
+int SUF(oracle_step_ext)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr, OracleEnv *envs,
+                         const double *action, int episode, OracleDebug *dbg, int n_threads, const float *ext_u) {
   if (!m || !cfg || !envs || !action || n <= 0 || cfg->observation_history > ORACLE_MAX_HIST) return -1;
 #ifdef _OPENMP
   if (n_threads <= 0) n_threads = omp_get_max_threads();
 #pragma omp parallel for num_threads(n_threads) schedule(static)
 #endif
-  for (int i = 0; i < n; i++) env_step(m, cfg, dr ? dr + i : NULL, envs + i, action + NU * i, episode, dbg ? dbg + i : NULL);
+  for (int i = 0; i < n; i++) {
+    g_ext = ext_u ? ext_u + (size_t)PUPPER_NRAND * i : NULL;
+    env_step(m, cfg, dr ? dr + i : NULL, envs + i, action + NU * i, episode, dbg ? dbg + i : NULL);
+    g_ext = NULL;
+  }
   return 0;
+}
+int SUF(oracle_step)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr, OracleEnv *envs,
+                     const double *action, int episode, OracleDebug *dbg, int n_threads) {
+  return SUF(oracle_step_ext)(m, cfg, n, dr, envs, action, episode, dbg, n_threads, NULL);
 }

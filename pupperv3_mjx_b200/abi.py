@@ -14,11 +14,13 @@ from typing import Dict, Mapping, Optional, Sequence
 
 import numpy as np
 
-from .mjcf import CompiledModel
+from .mjcf import CompiledModel, UnsupportedModelError
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 NBODY, NQ, NV, NU, NLEG, NSPHERE, NSITE = 14, 19, 18, 12, 4, 8, 5
-MAX_BOX, MAX_CON, MAX_PAIRS, MAX_LAT = 32, 8, 8, 8
+MAX_BOX, MAX_CON, MAX_PAIRS, MAX_LAT = 32, 8, 8, 8  # storage bounds of the header's tables
+KERNEL_MAX_CON, KERNEL_MAX_PAIRS = 5, 4  # what the CUDA path accepts (include/pupper_env.h PUPPER_KERNEL_MAX_*)
+NRAND = 44  # uniform draws per env of one reset / step (PupperRand)
 NREWARD, NMETRIC, OBS_DIM = 18, 19, 36
 
 # Reward terms in the order the reference builds its dict (environment.py:391-444).
@@ -165,7 +167,17 @@ DR_ROWS = {"friction": 1, "kp": 1, "kd": 1, "base_ipos": 3, "body_inertia": 39, 
 class PupperStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "reward", "done", "metrics", "dbg_x_pos", "dbg_x_rot", "dbg_xd_vel", "dbg_xd_ang",
-        "dbg_qfrc_actuator", "dbg_contact_dist", "dbg_contact_geom", "dbg_site_xpos", "dbg_qacc")]
+        "dbg_qfrc_actuator", "dbg_contact_dist", "dbg_contact_geom", "dbg_site_xpos", "dbg_qacc", "dbg_solver")]
+
+
+class PupperRand(C.Structure):
+    _fields_ = [("stride", i32), ("u", C.c_void_p)]
+
+
+# rows of PupperRand.u (include/pupper_env.h); reset reuses rows 0-3 for the start pose
+RAND_ROWS = {"kick_x": 0, "kick_y": 1, "kick_hit": 2, "act_latency": 3, "ang_noise": 4, "grav_noise": 7, "motor_noise": 10,
+             "last_act_noise": 22, "imu_latency": 34, "cmd_x": 35, "cmd_y": 36, "cmd_yaw": 37, "cmd_zero": 38, "cmd_small": 39,
+             "pitch": 42, "roll": 43, "start_x": 0, "start_y": 1, "start_z": 2, "start_yaw": 3}
 
 
 class PupperEpisode(C.Structure):
@@ -176,7 +188,7 @@ class PupperEpisode(C.Structure):
 
 EPISODE_ROWS = {"first_qpos": NQ, "first_qvel": NV, "first_warmstart": NV, "steps": 1, "truncation": 1,
                 "sum_reward": 1, "length": 1, "sum_metrics": NMETRIC, "episode_done": 1}
-N_TOTALS = 24  # [0] episodes finished, [1] sum_reward, [2] length, [3:22] metric sums, [22] done count, [23] env steps
+N_TOTALS = 24  # [0] episodes finished, [1] sum_reward, [2] length, [3:22] metric sums, [22] terminations (done without truncation), [23] reserved (always 0; keeps the all-reduced buffer 96 bytes)
 
 
 def _set(arr, values):
@@ -257,8 +269,13 @@ def model_desc(m: CompiledModel, position_control_kp: Optional[float] = None,
     d.max_geom_pairs = m.max_geom_pairs
     d.max_contact_points = m.max_contact_points
     d.frictionloss_rows = int(m.frictionloss_rows)
-    if not (1 <= m.max_geom_pairs <= MAX_PAIRS) or not (1 <= m.max_contact_points <= MAX_CON):
-        raise ValueError("max_geom_pairs / max_contact_points custom numerics must be in 1..8")
+    if m.max_geom_pairs < 0 or m.max_contact_points < 0:
+        raise UnsupportedModelError("the model has no max_geom_pairs / max_contact_points custom numeric (MJX's -1 = no limit): the CUDA "
+                                    "path needs explicit caps, 1..%d pairs per geom-type group and 1..%d contacts (the reference model "
+                                    "sets 4 and 5)" % (KERNEL_MAX_PAIRS, KERNEL_MAX_CON))
+    if not (1 <= m.max_geom_pairs <= KERNEL_MAX_PAIRS) or not (1 <= m.max_contact_points <= KERNEL_MAX_CON):
+        raise UnsupportedModelError(f"max_geom_pairs={m.max_geom_pairs} / max_contact_points={m.max_contact_points}: the CUDA path "
+                                    f"supports 1..{KERNEL_MAX_PAIRS} and 1..{KERNEL_MAX_CON}")
     return d
 
 

@@ -45,24 +45,34 @@ __device__ __forceinline__ float push_front_pick(float *row, int stride, int L, 
   return lag;
 }
 
+// jax.random.uniform's affine map of a raw [0, 1) draw (three separately rounded operations, as in `uniform`)
+__device__ __forceinline__ float affine_u(float f, float lo, float hi) {
+  return fmaxf(lo, __fadd_rn(__fmul_rn(f, __fsub_rn(hi, lo)), lo));
+}
+// One uniform draw: from the external-randoms table (row `row` of PupperRand, this env's column `ext`, rows `es` apart)
+// when one is given, else element `idx` of jax.random.uniform(key, ...) (threefry).
+__device__ __forceinline__ float draw(const float *ext, int es, int row, uint2 key, uint32_t idx, float lo, float hi) {
+  return ext ? affine_u(ext[(size_t)row * es], lo, hi) : uniform(key, idx, lo, hi);
+}
+
 // environment.py:246-272 (evaluated by one lane)
-__device__ __noinline__ void sample_command(const PupperEnvCfg &c, uint2 key, float cmd[3]) {
+__device__ __noinline__ void sample_command(const PupperEnvCfg &c, uint2 key, float cmd[3], const float *ext, int es) {
   uint2 k1 = split_key(key, 1), k2 = split_key(key, 2), k3 = split_key(key, 3), k4 = split_key(key, 4), k5 = split_key(key, 5);
-  float c0 = uniform(k1, 0, c.lin_vel_x[0], c.lin_vel_x[1]);
-  float c1 = uniform(k2, 0, c.lin_vel_y[0], c.lin_vel_y[1]);
-  float c2 = uniform(k3, 0, c.ang_vel_yaw[0], c.ang_vel_yaw[1]);
-  float zp = uniform(k4, 0, 0.f, 1.f);
+  float c0 = draw(ext, es, 35, k1, 0, c.lin_vel_x[0], c.lin_vel_x[1]);
+  float c1 = draw(ext, es, 36, k2, 0, c.lin_vel_y[0], c.lin_vel_y[1]);
+  float c2 = draw(ext, es, 37, k3, 0, c.ang_vel_yaw[0], c.ang_vel_yaw[1]);
+  float zp = draw(ext, es, 38, k4, 0, 0.f, 1.f);
   float thr = c.stand_still_command_threshold;
   if (zp < c.zero_command_probability) {
-    cmd[0] = uniform(k5, 0, -thr, thr); cmd[1] = uniform(k5, 1, -thr, thr); cmd[2] = uniform(k5, 2, -thr, thr);
+    cmd[0] = draw(ext, es, 39, k5, 0, -thr, thr); cmd[1] = draw(ext, es, 40, k5, 1, -thr, thr); cmd[2] = draw(ext, es, 41, k5, 2, -thr, thr);
   } else { cmd[0] = c0; cmd[1] = c1; cmd[2] = c2; }
 }
 
 // environment.py:274-298 (evaluated by one lane)
-__device__ __noinline__ void sample_body_orientation(const PupperEnvCfg &c, uint2 key, float out[3]) {
+__device__ __noinline__ void sample_body_orientation(const PupperEnvCfg &c, uint2 key, float out[3], const float *ext, int es) {
   uint2 kp = split_key(key, 1), kr = split_key(key, 2);
-  float pitch = __fmul_rn(uniform(kp, 0, -1.f, 1.f), c.maximum_pitch_command);
-  float roll = __fmul_rn(uniform(kr, 0, -1.f, 1.f), c.maximum_roll_command);
+  float pitch = __fmul_rn(draw(ext, es, 42, kp, 0, -1.f, 1.f), c.maximum_pitch_command);
+  float roll = __fmul_rn(draw(ext, es, 43, kr, 0, -1.f, 1.f), c.maximum_roll_command);
   const float pi = 3.14159274101257324f;
   float a1 = roll * pi / 360.f, a2 = pitch * pi / 360.f;
   float s1, c1, s2, c2;
@@ -83,7 +93,7 @@ struct ObsCtx {
 // _get_obs (environment.py:485-543). `rng` is info["rng"] on entry; returns the new info["rng"].
 // Updates the IMU buffer and the observation history in global memory.
 __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p, int e, int k, unsigned qm, int qbase, uint2 rng,
-                                         const StaleOut &so, const ObsCtx &oc, bool zero_history, bool valid) {
+                                         const StaleOut &so, const ObsCtx &oc, bool zero_history, bool valid, const float *ext, int es) {
   const PupperEnvCfg &c = sh.c;
   const int stride = p.st.stride;
   // split(rng, 6): lane 0 -> new rng, lane 1 -> ang key, lane 2 -> gravity key, lane 3 -> imu sample key
@@ -91,8 +101,8 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
   uint2 k_motor = split_key(rng, 3u), k_act = split_key(rng, 4u);
   uint2 new_rng = qbcast2(kmine, 0, qm, qbase), k_ang = qbcast2(kmine, 1, qm, qbase), k_grav = qbcast2(kmine, 2, qm, qbase);
   // one draw per lane: lanes 0-2 angular-velocity noise component k, lane 3 the IMU latency draw
-  float uA = uniform(k < 3 ? k_ang : kmine, k < 3 ? (uint32_t)k : 0u, k < 3 ? -1.f : 0.f, 1.f);
-  float uB = uniform(k_grav, (uint32_t)k, -1.f, 1.f);
+  float uA = draw(ext, es, k < 3 ? 4 + k : 34, k < 3 ? k_ang : kmine, k < 3 ? (uint32_t)k : 0u, k < 3 ? -1.f : 0.f, 1.f);
+  float uB = draw(ext, es, k < 3 ? 7 + k : 7, k_grav, (uint32_t)k, -1.f, 1.f);
   float an_mine = __fmul_rn(uA, c.angular_velocity_noise), gn_mine = __fmul_rn(uB, c.gravity_noise);
   float an[3], gn[3];
 #pragma unroll
@@ -150,8 +160,8 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     const int u = 3 * k + j;
-    float mn = __fmul_rn(uniform(k_motor, (uint32_t)u, -1.f, 1.f), c.motor_angle_noise);
-    float ln = __fmul_rn(uniform(k_act, (uint32_t)u, -1.f, 1.f), c.last_action_noise);
+    float mn = __fmul_rn(draw(ext, es, 10 + u, k_motor, (uint32_t)u, -1.f, 1.f), c.motor_angle_noise);
+    float ln = __fmul_rn(draw(ext, es, 22 + u, k_act, (uint32_t)u, -1.f, 1.f), c.last_action_noise);
     if (valid) obs[12 + u] = clip100(oc.ql[j] - c.default_pose[u] + mn);
     if (valid) obs[24 + u] = clip100(oc.last_act[j] + ln);
   }
@@ -196,6 +206,9 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   const PupperEnvCfg &c = sh.c;
   EnvShared &es = sh.env[el];
   const int stride = p.st.stride;
+  // external randoms: only the debug / parity instantiation looks at them (pupper_step routes calls that pass them there)
+  const float *ext = (DBG && p.has_rand) ? p.rand.u + e : nullptr;
+  const int ext_s = (DBG && p.has_rand) ? p.rand.stride : 0;
 
   // ---- stage the per-env DR leaves (or the nominal values) in shared memory --------------------------
   // (two phases so the up-to-15 global loads of a lane are all in flight before the first is consumed)
@@ -248,9 +261,9 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
 #pragma unroll
     for (int i = 0; i < 7; i++) L.qb[i] = c.init_q[i];
 #pragma unroll
-    for (int i = 0; i < 3; i++) L.qb[i] = uniform(kp, (uint32_t)i, c.start_pos_min[i], c.start_pos_max[i]);
+    for (int i = 0; i < 3; i++) L.qb[i] = draw(ext, ext_s, i, kp, (uint32_t)i, c.start_pos_min[i], c.start_pos_max[i]);
     {
-      float yaw = uniform(ky, 0u, -3.14159274101257324f, 3.14159274101257324f);
+      float yaw = draw(ext, ext_s, 3, ky, 0u, -3.14159274101257324f, 3.14159274101257324f);
       float s, cs;
       sincosf(yaw / 2.f, &s, &cs);
       L.qb[3] = cs; L.qb[4] = 0.f; L.qb[5] = 0.f; L.qb[6] = s;
@@ -267,12 +280,13 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
 #pragma unroll
     for (int j = 0; j < 3; j++) L.wl[j] = al[j];
     float cmd[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
-    if (k == 0) { sample_command(c, k_cmd, cmd); sample_body_orientation(c, k_ori, dz); }
+    if (k == 0) { sample_command(c, k_cmd, cmd, ext, ext_s); sample_body_orientation(c, k_ori, dz, ext, ext_s); }
 #pragma unroll
     for (int i = 0; i < 3; i++) { oc.command[i] = __shfl_sync(qm, cmd[i], qbase); oc.desired_z[i] = __shfl_sync(qm, dz[i], qbase); }
 #pragma unroll
     for (int j = 0; j < 3; j++) { oc.last_act[j] = 0.f; oc.ql[j] = L.ql[j]; }
-    rng = get_obs(sh, p, e, k, qm, qbase, k_rng, so, oc, true, valid);
+    rng = get_obs(sh, p, e, k, qm, qbase, k_rng, so, oc, true, valid, ext, ext_s);
+    if (ext) rng = key;  // external randoms: info["rng"] is never consumed; it keeps the env's key
     // info / state
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -334,7 +348,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     cmd_rng = K1;
     // S2/S3 draws, one per lane: kick x, kick y, kick Bernoulli, latency pick
     // (lane 0: kick x, lane 1: kick y, lane 2: latency pick with key 4, lane 3: Bernoulli with its own key 3)
-    float u = uniform(k < 2 ? K2 : (k == 2 ? k4 : kmine), k == 1 ? 1u : 0u, k < 2 ? -1.f : 0.f, 1.f);
+    float u = draw(ext, ext_s, k < 2 ? k : (k == 2 ? 3 : 2), k < 2 ? K2 : (k == 2 ? k4 : kmine), k == 1 ? 1u : 0u, k < 2 ? -1.f : 0.f, 1.f);
     float kv = __fmul_rn(u, c.kick_vel);
     float hit = __shfl_sync(qm, (u < c.kick_probability) ? 1.f : 0.f, qbase + 3);
     kick0 = __fmul_rn(__shfl_sync(qm, kv, qbase + 0), hit);
@@ -386,7 +400,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     kick0 = es.lv_kick[0]; kick1 = es.lv_kick[1];
     cmd_rng = make_uint2(es.lv_cmd_rng[0], es.lv_cmd_rng[1]);
     // S6 observation (reads the not-yet-updated last_act / command / desired_z)
-    rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false, valid);
+    rng = get_obs(sh, p, e, k, qm, qbase, rng, so, oc, false, valid, ext, ext_s);
   }
 
   // ---- write back the physics state -------------------------------------------------------------------------
@@ -410,7 +424,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     if (valid) p.st.qvel[(size_t)i * stride + e] = v;
     if (valid) p.st.qacc_warmstart[(size_t)i * stride + e] = w;
   }
-  if (k == 0) { if (valid) p.st.rng[e] = rng.x; if (valid) p.st.rng[stride + e] = rng.y; }
+  if (k == 0 && (RESET || !ext)) { if (valid) p.st.rng[e] = rng.x; if (valid) p.st.rng[stride + e] = rng.y; }  // a step with external randoms leaves the key alone
 
   if (DBG) {
     if (p.out.dbg_x_pos) {
@@ -439,6 +453,9 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
       float *o = p.out.dbg_qacc + (size_t)e * 18;
       for (int j = 0; j < 3; j++) if (valid) o[6 + 3 * k + j] = dbg.qacc_l[j];
       if (k == 0) for (int d = 0; d < 6; d++) if (valid) o[d] = dbg.qacc_b[d];
+    }
+    if (p.out.dbg_solver && !RESET && k == 0) {
+      for (int i = 0; i < 8; i++) if (valid) p.out.dbg_solver[(size_t)e * 8 + i] = dbg.solver[i];
     }
     if (p.out.dbg_site_xpos) {
       float *o = p.out.dbg_site_xpos + (size_t)e * 15;
@@ -579,7 +596,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   const bool resample = step > c.resample_velocity_step;
   if (__any_sync(qm, resample)) {
     float cmd[3] = {0.f, 0.f, 0.f}, dz[3] = {0.f, 0.f, 0.f};
-    if (k == 0 && resample) { sample_command(c, cmd_rng, cmd); sample_body_orientation(c, cmd_rng, dz); }
+    if (k == 0 && resample) { sample_command(c, cmd_rng, cmd, ext, ext_s); sample_body_orientation(c, cmd_rng, dz, ext, ext_s); }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       float cv = __shfl_sync(qm, cmd[i], qbase), dv = __shfl_sync(qm, dz[i], qbase);
@@ -744,6 +761,7 @@ int pupper_sizeof(int which) {
     case 3: return (int)sizeof(PupperDR);
     case 4: return (int)sizeof(PupperStepOut);
     case 5: return (int)sizeof(PupperEpisode);
+    case 6: return (int)sizeof(PupperRand);
     default: return -1;
   }
 }
@@ -839,7 +857,7 @@ static int check_common(const PupperModel *model, int n_envs, const PupperDR *dr
 }
 
 static pupper::KParams make_params(const PupperModel *model, int n_envs, const PupperDR *dr, const PupperState *st, const float *action,
-                                   const uint32_t *keys, const PupperStepOut *out, const PupperEpisode *ep) {
+                                   const uint32_t *keys, const PupperStepOut *out, const PupperEpisode *ep, const PupperRand *rand) {
   pupper::KParams p;
   memset(&p, 0, sizeof(p));
   p.model = model->d_desc;
@@ -852,11 +870,12 @@ static pupper::KParams make_params(const PupperModel *model, int n_envs, const P
   p.keys = keys;
   p.out = *out;
   if (ep) { p.ep = *ep; p.has_ep = 1; }
+  if (rand) { p.rand = *rand; p.has_rand = 1; }
   return p;
 }
 
 static bool wants_debug(const PupperStepOut *o) {
-  return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc;
+  return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc || o->dbg_solver;
 }
 // the x / xd taps come as a group, and so do the two contact taps
 static bool debug_ok(const PupperStepOut *o) {
@@ -867,14 +886,15 @@ static bool debug_ok(const PupperStepOut *o) {
 }
 
 int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, const PupperDR *dr, PupperState *state, PupperStepOut *out,
-                 PupperEpisode *episode, pupper_stream_t stream) {
+                 PupperEpisode *episode, const PupperRand *ext_rand, pupper_stream_t stream) {
   int rc = check_common(model, n_envs, dr, state, out, episode);
   if (rc != PUPPER_OK) return rc;
   if (!keys || !debug_ok(out)) return PUPPER_EINVAL;
-  pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode);
+  if (ext_rand && (!ext_rand->u || ext_rand->stride < n_envs)) return PUPPER_EINVAL;
+  pupper::KParams p = make_params(model, n_envs, dr, state, nullptr, keys, out, episode, ext_rand);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<true, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
+  if (wants_debug(out) || ext_rand) pupper::env_kernel<true, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   else pupper::env_kernel<true, false><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_reset launch");
@@ -882,15 +902,16 @@ int pupper_reset(const PupperModel *model, int n_envs, const uint32_t *keys, con
   return PUPPER_OK;
 }
 
-int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, PupperState *state, const float *action, PupperStepOut *out,
-                PupperEpisode *episode, pupper_stream_t stream) {
+int pupper_step(const PupperModel *model, int n_envs, const PupperDR *dr, PupperState *state, const float *action, const PupperRand *ext_rand,
+                PupperStepOut *out, PupperEpisode *episode, pupper_stream_t stream) {
   int rc = check_common(model, n_envs, dr, state, out, episode);
   if (rc != PUPPER_OK) return rc;
   if (!action || !debug_ok(out)) return PUPPER_EINVAL;
-  pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode);
+  if (ext_rand && (!ext_rand->u || ext_rand->stride < n_envs)) return PUPPER_EINVAL;
+  pupper::KParams p = make_params(model, n_envs, dr, state, action, nullptr, out, episode, ext_rand);
   const int grid = (n_envs + pupper::kEnvsPerBlock - 1) / pupper::kEnvsPerBlock;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (wants_debug(out)) pupper::env_kernel<false, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
+  if (wants_debug(out) || ext_rand) pupper::env_kernel<false, true><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   else pupper::env_kernel<false, false><<<grid, pupper::kBlock, model->smem_bytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "pupper_step launch");

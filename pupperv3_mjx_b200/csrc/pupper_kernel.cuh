@@ -28,25 +28,16 @@ namespace pupper {
 #define PUPPER_BLOCK 128
 #endif
 #ifndef PUPPER_PHASE_SYNC
-#define PUPPER_PHASE_SYNC 0
+#define PUPPER_PHASE_SYNC 1
 #endif
 // A/B switches of individual optimisations (tools/jobs/ab.sh builds the variants and times them on one box)
-#ifndef PUPPER_ROWS_BCAST
-#define PUPPER_ROWS_BCAST 0  // single-source shuffle instead of the quad butterfly in contact_rows: fewer instructions, yet 1.5-2.3 % SLOWER (A/B on one B200)
-#endif
-#ifndef PUPPER_LS_PEEL
-#define PUPPER_LS_PEEL 1  // line search: the Newton point of p0 (stage 0) is ONE step size, evaluated alone instead of as three equal points
-#endif
-#ifndef PUPPER_LIM_UNIFORM
-#define PUPPER_LIM_UNIFORM 1  // limit rows in the line search behind one warp-uniform test instead of three divergent ones per pass
-#endif
 #ifndef PUPPER_ZFOLD
 #define PUPPER_ZFOLD 1   // structural zeros folded by hand (the compiler may not drop 0*x terms)
 #endif
 
-// Experiment switch: CTA barriers at phase boundaries to keep a CTA's warps in step so they share
-// instruction-cache fills (`no_instruction` is a top stall reason, profiles/r1_summary.md).  Measured
-// A/B on B200: no difference at 4096 or 65,536 envs, so it is off.
+// CTA barriers at phase boundaries keep a CTA's warps within one instruction-cache window of each other, so a line fetched
+// by one warp serves the others (tools/microbench/fetch_probe.cu: warps of an SM that run a 96 KB loop body in step issue 4x
+// the instructions per clock of warps spread over it).  A/B on B200 with the round-2 kernel: +2.1 % at 65,536 envs, -0.4 % at 4096; twice as many barriers: -0.3 %.
 #if PUPPER_PHASE_SYNC
 #define PHASE_SYNC() __syncthreads()
 #else
@@ -72,6 +63,8 @@ struct KParams {
   PupperStepOut out;
   PupperEpisode ep;
   int has_ep;
+  PupperRand rand;  // external randoms (debug / parity instantiation only)
+  int has_rand;
 };
 
 struct ContactSlot {  // one ACTIVE contact (dist < 0) of an env, shared by the quad
@@ -393,6 +386,7 @@ __device__ __forceinline__ StaleOut load_stale(const struct EnvShared &es, int k
 struct DbgOut {  // only filled when DBG
   V3 pos[3]; Q4 rot[3]; V3 ang[3], vel[3];
   float qacc_b[6], qacc_l[3];
+  int solver[8];  // PupperStepOut.dbg_solver (replicated over the quad)
 };
 
 __device__ __forceinline__ StaleOut load_stale(const EnvShared &es, int k) {
@@ -1505,15 +1499,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         z1 = fmaf(lin, neg ? fc[j][1] : fc[j][3], z1);
         z2 = fmaf(-lin, 0.5f * hl[j] * hl[j] * fD[j], z2);
       }
-#if !PUPPER_LIM_UNIFORM
-      if (lsign[j] != 0.f) {
-        const float ja = lJ[j], jv = lsign[j] * hl[j];
-        const float on = ja < 0.f ? 1.f : 0.f;
-        z0 = fmaf(on, 0.5f * ja * ja * lD[j], z0); z1 = fmaf(on, jv * ja * lD[j], z1); z2 = fmaf(on, 0.5f * jv * jv * lD[j], z2);
-      }
-#endif
     }
-#if PUPPER_LIM_UNIFORM
     const bool lim_w = __any_sync(qm, (lsign[0] != 0.f) | (lsign[1] != 0.f) | (lsign[2] != 0.f));
     if (lim_w) {
 #pragma unroll
@@ -1523,7 +1509,6 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         z0 = fmaf(on, 0.5f * ja * ja * lD[j], z0); z1 = fmaf(on, jv * ja * lD[j], z1); z2 = fmaf(on, 0.5f * jv * jv * lD[j], z2);
       }
     }
-#endif
 #pragma unroll
     for (int c = 0; c < kMaxCon; c++) {
       const bool con = c < ncon;
@@ -1557,19 +1542,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             s2[p] = fmaf(-lin, qc, s2[p]);
           }
         }
-#if !PUPPER_LIM_UNIFORM
-        if (lsign[j] != 0.f) {
-          const float ja = lJ[j], jv = lsign[j] * hl[j];
-          const float qa = 0.5f * ja * ja * lD[j], qb = jv * ja * lD[j], qc = 0.5f * jv * jv * lD[j];
-#pragma unroll
-          for (int p = 0; p < NP; p++) {
-            const float on = fmaf(a[p], jv, ja) < 0.f ? 1.f : 0.f;
-            s0[p] = fmaf(on, qa, s0[p]); s1[p] = fmaf(on, qb, s1[p]); s2[p] = fmaf(on, qc, s2[p]);
-          }
-        }
-#endif
       }
-#if PUPPER_LIM_UNIFORM
       if (lim_w) {  // some joint of this warp is past a limit (rare); rows that are not have lD = 0, ja = jv = 0: they add zeros
 #pragma unroll
         for (int j = 0; j < 3; j++) {
@@ -1582,7 +1555,6 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
           }
         }
       }
-#endif
 #pragma unroll
       for (int c = 0; c < kMaxCon; c++) {  // unrolled, zero coefficients past the env's contacts: no loop or divergence branches
         const float4 q4 = lsq[c * kBlock];
@@ -1609,8 +1581,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     }
     lo = p0; hi = p0;
     bool swap = true, ls_on = true;
+    int ls_it = 0;  // DBG: bracket refinements this env ran (MJX's loop counter)
     const int nstage = 1 + m.ls_iterations;  // stage 0: the Newton point of p0; stages 1..: bracket refinements
-#if PUPPER_LS_PEEL
     {
       const float a1[1] = {p0.alpha - p0.d0 / p0.d1};
       LSPoint pt1[1];
@@ -1626,6 +1598,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       a3[0] = lo.alpha - lo.d0 / lo.d1; a3[1] = hi.alpha - hi.d0 / hi.d1; a3[2] = 0.5f * (lo.alpha + hi.alpha);
       LSPoint pt[3];
       evalN(std::integral_constant<int, 3>{}, a3, pt);
+      if (DBG && ls_on) ls_it++;
       if (ls_on) {
         const LSPoint lon = pt[0], hin = pt[1], mid = pt[2];
         const bool s1 = in_bracket(lo, lon); lo = ls_select(s1, lon, lo);
@@ -1637,36 +1610,24 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         swap = s1 | s2 | s3 | t1 | t2 | t3;
       }
     }
-#else
-#pragma unroll 1
-    for (int stage = 0; stage < nstage; stage++) {
-      float a3[3];
-      if (stage == 0) { a3[0] = a3[1] = a3[2] = p0.alpha - p0.d0 / p0.d1; }
-      else {
-        if (!swap || ((lo.d0 < 0.f) && (lo.d0 > -gtol)) || ((hi.d0 > 0.f) && (hi.d0 < gtol))) ls_on = false;
-        if (!__any_sync(qm, ls_on)) break;  // warp-uniform exit; finished envs idle through the remaining stages
-        a3[0] = lo.alpha - lo.d0 / lo.d1; a3[1] = hi.alpha - hi.d0 / hi.d1; a3[2] = 0.5f * (lo.alpha + hi.alpha);
-      }
-      LSPoint pt[3];
-      evalN(std::integral_constant<int, 3>{}, a3, pt);
-      if (stage == 0) {
-        lo = pt[0];
-        if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
-      } else if (ls_on) {
-        const LSPoint lon = pt[0], hin = pt[1], mid = pt[2];
-        const bool s1 = in_bracket(lo, lon); lo = ls_select(s1, lon, lo);
-        const bool s2 = in_bracket(lo, mid); lo = ls_select(s2, mid, lo);
-        const bool s3 = in_bracket(lo, hin); lo = ls_select(s3, hin, lo);
-        const bool t1 = in_bracket(hi, hin); hi = ls_select(t1, hin, hi);
-        const bool t2 = in_bracket(hi, mid); hi = ls_select(t2, mid, hi);
-        const bool t3 = in_bracket(hi, lon); hi = ls_select(t3, lon, hi);
-        swap = s1 | s2 | s3 | t1 | t2 | t3;
-      }
-    }
-#endif
     bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
     alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
     if (!improved) alpha = 0.f;
+    if (DBG && want_stale && dbg) {  // solver decisions (PupperStepOut.dbg_solver)
+      int fz = 0, lim = 0, con = 0;
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        fz |= (fJ[j] <= -rff[j] ? 2 : (fJ[j] >= rff[j] ? 3 : 1)) << (2 * (3 * k + j));
+        lim |= ((lsign[j] != 0.f && lJ[j] < 0.f) ? 1 : 0) << (3 * k + j);
+      }
+      for (int c = 0; c < ncon; c++) con |= (rowJ[c * kBlock] < 0.f ? 1 : 0) << (4 * c + k);
+#pragma unroll
+      for (int sft = 1; sft <= 2; sft <<= 1) {
+        fz |= __shfl_xor_sync(qm, fz, sft); lim |= __shfl_xor_sync(qm, lim, sft); con |= __shfl_xor_sync(qm, con, sft);
+      }
+      dbg->solver[0] = use_w ? 1 : 0; dbg->solver[1] = ls_it; dbg->solver[2] = ncon; dbg->solver[3] = fz; dbg->solver[4] = lim;
+      dbg->solver[5] = con; dbg->solver[6] = __float_as_int(alpha); dbg->solver[7] = n_ss;
+    }
   }
 #pragma unroll
   for (int d = 0; d < 6; d++) ab[d] = fmaf(alpha, hb[d], xb[d]);

@@ -32,9 +32,33 @@ __device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) {  // s*a + b
 }
 __device__ __forceinline__ float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
+#ifndef PUPPER_F2
+#define PUPPER_F2 1  // packed FP32x2 (FFMA2 / FADD2 / FMUL2, sm_100) for 6-vector arithmetic: same IEEE results per element, half the
+#endif               // instructions to fetch -- the step kernel is instruction-fetch bound in its straight-line phases
+#if PUPPER_F2
+// a 6-vector as three register pairs: (a.x, a.y) (a.z, l.x) (l.y, l.z)
+struct P6 { float2 p0, p1, p2; };
+__device__ __forceinline__ P6 pack6(S6 v) { return P6{make_float2(v.a.x, v.a.y), make_float2(v.a.z, v.l.x), make_float2(v.l.y, v.l.z)}; }
+__device__ __forceinline__ S6 unpack6(P6 p) { return S6{V3{p.p0.x, p.p0.y, p.p1.x}, V3{p.p1.y, p.p2.x, p.p2.y}}; }
+__device__ __forceinline__ S6 operator+(S6 a, S6 b) {
+  const P6 x = pack6(a), y = pack6(b);
+  return unpack6(P6{__fadd2_rn(x.p0, y.p0), __fadd2_rn(x.p1, y.p1), __fadd2_rn(x.p2, y.p2)});
+}
+__device__ __forceinline__ S6 operator*(float s, S6 a) {
+  const P6 x = pack6(a);
+  const float2 ss = make_float2(s, s);
+  return unpack6(P6{__fmul2_rn(ss, x.p0), __fmul2_rn(ss, x.p1), __fmul2_rn(ss, x.p2)});
+}
+__device__ __forceinline__ S6 fma6(float s, S6 a, S6 b) {
+  const P6 x = pack6(a), y = pack6(b);
+  const float2 ss = make_float2(s, s);
+  return unpack6(P6{__ffma2_rn(ss, x.p0, y.p0), __ffma2_rn(ss, x.p1, y.p1), __ffma2_rn(ss, x.p2, y.p2)});
+}
+#else
 __device__ __forceinline__ S6 operator+(S6 a, S6 b) { return S6{a.a + b.a, a.l + b.l}; }
 __device__ __forceinline__ S6 operator*(float s, S6 a) { return S6{s * a.a, s * a.l}; }
 __device__ __forceinline__ S6 fma6(float s, S6 a, S6 b) { return S6{fma3(s, a.a, b.a), fma3(s, a.l, b.l)}; }
+#endif
 __device__ __forceinline__ float dot6(S6 a, S6 b) { return dot(a.a, b.a) + dot(a.l, b.l); }
 // motion cross product u x v  = [u.a x v.a, u.l x v.a + u.a x v.l]
 __device__ __forceinline__ S6 motion_cross(S6 u, S6 v) { return S6{cross(u.a, v.a), cross(u.l, v.a) + cross(u.a, v.l)}; }

@@ -40,8 +40,8 @@ def load_library() -> C.CDLL:
         lib.pupper_last_cuda_error.restype = C.c_char_p
         lib.pupper_model_create.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         lib.pupper_model_destroy.argtypes = [C.c_void_p]
-        lib.pupper_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.pupper_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_reset.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.pupper_last_launch_count.argtypes = [C.c_void_p]
         lib.pupper_state_rows.argtypes = [C.c_void_p, C.c_void_p]
         lib.pupper_probe_ffma.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -49,7 +49,7 @@ def load_library() -> C.CDLL:
         lib.pupper_policy_destroy.argtypes = [C.c_void_p]
         lib.pupper_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut,
-                               abi.PupperEpisode)):
+                               abi.PupperEpisode, abi.PupperRand)):
             if lib.pupper_sizeof(i) != C.sizeof(s):
                 raise PupperError(f"ABI struct {s.__name__}: library {lib.pupper_sizeof(i)} B vs ctypes {C.sizeof(s)} B")
         if lib.pupper_abi_version() != abi.ABI_VERSION:
@@ -173,9 +173,9 @@ class EnvRuntime:
             mc = model_desc.max_contact_points
             shapes = {"dbg_x_pos": (13, 3), "dbg_x_rot": (13, 4), "dbg_xd_vel": (13, 3), "dbg_xd_ang": (13, 3),
                       "dbg_qfrc_actuator": (18,), "dbg_contact_dist": (mc,), "dbg_contact_geom": (mc, 2),
-                      "dbg_site_xpos": (5, 3), "dbg_qacc": (18,)}
+                      "dbg_site_xpos": (5, 3), "dbg_qacc": (18,), "dbg_solver": (8,)}
             for name, shp in shapes.items():
-                dt = torch.int32 if name == "dbg_contact_geom" else torch.float32
+                dt = torch.int32 if name in ("dbg_contact_geom", "dbg_solver") else torch.float32
                 t = torch.zeros((self.n_envs,) + shp, dtype=dt, device=self.device)
                 self.dbg[name] = t
                 setattr(self.out, name, t.data_ptr())
@@ -240,26 +240,41 @@ class EnvRuntime:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, keys: torch.Tensor):
+    def _rand_struct(self, ext_rand: Optional[torch.Tensor]):
+        """External randoms ``[44, n_envs]`` float32 in [0, 1) (rows: ``abi.RAND_ROWS``) -> PupperRand, or None."""
+        if ext_rand is None:
+            return None
+        if ext_rand.device != self.device or ext_rand.dtype != torch.float32 or ext_rand.dim() != 2 \
+                or ext_rand.shape[0] != abi.NRAND or ext_rand.shape[1] < self.n_envs or ext_rand.stride(1) != 1:
+            raise PupperError(f"ext_rand must be a float32 CUDA tensor of shape [{abi.NRAND}, >= n_envs] with unit column stride")
+        r = abi.PupperRand()
+        r.stride, r.u = int(ext_rand.stride(0)), ext_rand.data_ptr()
+        self._rand_keepalive = ext_rand
+        return r
+
+    def reset(self, keys: torch.Tensor, ext_rand: Optional[torch.Tensor] = None):
         keys = keys.to(device=self.device).contiguous()
         if keys.dtype not in (torch.int32, torch.uint32) or keys.numel() != 2 * self.n_envs:
             raise PupperError("keys must be a 32-bit integer tensor of shape [n_envs, 2]")
         self._keys = keys
+        rand = self._rand_struct(ext_rand)
         with torch.cuda.device(self.device):
             rc = self.lib.pupper_reset(self._model, self.n_envs, keys.data_ptr(),
                                        C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
-                                       C.byref(self.out), C.byref(self.episode) if self.episode else None, self._stream())
+                                       C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                       C.byref(rand) if rand is not None else None, self._stream())
         _check(self.lib, rc, "pupper_reset")
         self.launches += self.lib.pupper_last_launch_count(self._model)
 
-    def step(self, action: torch.Tensor):
+    def step(self, action: torch.Tensor, ext_rand: Optional[torch.Tensor] = None):
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
                 or action.numel() != self.n_envs * abi.NU:
             raise PupperError("action must be a contiguous float32 CUDA tensor of shape [n_envs, 12] on the env's device")
+        rand = self._rand_struct(ext_rand)
         with torch.cuda.device(self.device):
             rc = self.lib.pupper_step(self._model, self.n_envs, C.byref(self._dr_struct) if self._dr_struct else None,
-                                      C.byref(self.state), action.data_ptr(), C.byref(self.out),
-                                      C.byref(self.episode) if self.episode else None, self._stream())
+                                      C.byref(self.state), action.data_ptr(), C.byref(rand) if rand is not None else None,
+                                      C.byref(self.out), C.byref(self.episode) if self.episode else None, self._stream())
         _check(self.lib, rc, "pupper_step")
         self.launches += 1
 
@@ -330,7 +345,7 @@ class EnvRuntime:
                     return self.step_host(h_action, h_out, chunks)
             self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
             rc = self.lib.pupper_step(self._model, n, C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
-                                      self._d_act.data_ptr(), C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                      self._d_act.data_ptr(), None, C.byref(self.out), C.byref(self.episode) if self.episode else None,
                                       cur.cuda_stream)
             if rc != 0:
                 _check(self.lib, rc, "pupper_step")
@@ -349,7 +364,7 @@ class EnvRuntime:
                     ev_in.record(self._s_in)
                 cur.wait_event(ev_in)
                 rc = self.lib.pupper_step(model, cnt, C.byref(dr) if dr is not None else None, C.byref(st),
-                                          self._d_act.data_ptr() + 4 * e0 * abi.NU, C.byref(so),
+                                          self._d_act.data_ptr() + 4 * e0 * abi.NU, None, C.byref(so),
                                           C.byref(ep) if ep is not None else None, cur.cuda_stream)
                 _check(self.lib, rc, "pupper_step")
                 self.launches += 1

@@ -77,3 +77,34 @@ def dr_struct(sys_v):
     d["body_inertia"] = sys_v.body_inertia[:, 1:].reshape(B, 39)
     d["body_mass"] = sys_v.body_mass[:, 1:]
     return d
+
+
+def raw_uniform(key, n):
+    """n raw [0, 1) uniforms of jax.random.uniform(key, (n,)) before its affine map (lo = 0, hi = 1 is the identity)."""
+    return prng.uniform(key, n, 0.0, 1.0).astype(np.float32)
+
+
+def ext_rand_from_step_keys(rng_keys):
+    """External-randoms table [n, 44] (include/pupper_env.h PupperRand rows) holding exactly the draws the reference's key
+    tree makes in one env step from info["rng"] = rng_keys[i] (environment.py:349-361, 499-523, 256-269, 291-293)."""
+    n = rng_keys.shape[0]
+    u = np.zeros((n, 44), np.float32)
+    for i in range(n):
+        k = prng.split(rng_keys[i], 5)                     # rng', cmd_rng, kick noise, kick Bernoulli, action latency
+        u[i, 0:2] = raw_uniform(k[2], 2)
+        u[i, 2] = raw_uniform(k[3], 1)[0]
+        u[i, 3] = raw_uniform(k[4], 1)[0]
+        o = prng.split(k[0], 6)                            # _get_obs: rng'', ang, gravity, motor, last action, IMU latency
+        u[i, 4:7] = raw_uniform(o[1], 3)
+        u[i, 7:10] = raw_uniform(o[2], 3)
+        u[i, 10:22] = raw_uniform(o[3], 12)
+        u[i, 22:34] = raw_uniform(o[4], 12)
+        u[i, 34] = raw_uniform(o[5], 1)[0]
+        c = prng.split(k[1], 6)                            # sample_command
+        for j in range(4):
+            u[i, 35 + j] = raw_uniform(c[1 + j], 1)[0]
+        u[i, 39:42] = raw_uniform(c[5], 3)
+        b = prng.split(k[1], 3)                            # sample_body_orientation (same key, 3-way split)
+        u[i, 42] = raw_uniform(b[1], 1)[0]
+        u[i, 43] = raw_uniform(b[2], 1)[0]
+    return u

@@ -20,12 +20,16 @@ class Harness:
             self.rt.set_dr(dr)
         self.cfg = env.env_cfg
 
-    def reset(self, keys):
-        self.rt.reset(torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).cuda())
+    def _ext(self, ext_rand):
+        """[n, 44] host table (the oracle's layout) -> device [44, n] (PupperRand layout)."""
+        return None if ext_rand is None else _dev(np.ascontiguousarray(ext_rand, dtype=np.float32).T, self.rt.device)
+
+    def reset(self, keys, ext_rand=None):
+        self.rt.reset(torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).cuda(), self._ext(ext_rand))
         torch.cuda.synchronize()
 
-    def step(self, action):
-        self.rt.step(_dev(action, self.rt.device))
+    def step(self, action, ext_rand=None):
+        self.rt.step(_dev(action, self.rt.device), self._ext(ext_rand))
         torch.cuda.synchronize()
 
     def load_state(self, envs):

@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_ctypes_mirror():
     lib = runtime.load_library()
-    for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut, abi.PupperEpisode)):
+    for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut, abi.PupperEpisode,
+                           abi.PupperRand)):
         assert lib.pupper_sizeof(i) == C.sizeof(s)
     assert lib.pupper_abi_version() == abi.ABI_VERSION
     assert b"invalid" in lib.pupper_strerror(-1)
@@ -34,8 +35,8 @@ def test_struct_sizes_match_ctypes_mirror():
 def test_entry_points_reject_bad_arguments_without_a_gpu():
     lib = runtime.load_library()
     assert lib.pupper_model_create(None, None, 0, None) == -1
-    assert lib.pupper_step(None, 4, None, None, None, None, None, None) == -1
-    assert lib.pupper_reset(None, 4, None, None, None, None, None, None) == -1
+    assert lib.pupper_step(None, 4, None, None, None, None, None, None, None) == -1
+    assert lib.pupper_reset(None, 4, None, None, None, None, None, None, None) == -1
     env = common.make_env()
     rows = (C.c_int32 * 14)()
     assert lib.pupper_state_rows(C.byref(env.env_cfg), rows) == 0
@@ -164,3 +165,19 @@ def test_env_ranges_of_the_pipelined_host_path():
     assert env_ranges(65536, 4, wave) == [(0, 18944), (18944, 18944), (37888, 18944), (56832, 8704)]
     with pytest.raises(ValueError):
         env_ranges(0, 1, wave)
+
+
+def test_contact_caps_outside_the_kernel_range_are_rejected_with_a_clear_message():
+    """The CUDA path takes 1..4 geom pairs per group and 1..5 contacts; MJX's -1 (no limit) gets its own message."""
+    import xml.etree.ElementTree as ET
+    from pupperv3_mjx_b200 import utils
+    tree = utils.set_mjx_custom_options(ET.parse(common.MODEL_PATH), max_contact_points=8, max_geom_pairs=8)
+    with pytest.raises(mjcf.UnsupportedModelError, match="supports 1..4 and 1..5"):
+        environment.PupperV3Env(**dict(common.env_kwargs(), path=tree))
+    tree = ET.parse(common.MODEL_PATH)
+    custom = tree.getroot().find("custom")
+    for el in list(custom):
+        if el.get("name") in ("max_contact_points", "max_geom_pairs"):
+            custom.remove(el)
+    with pytest.raises(mjcf.UnsupportedModelError, match="no limit"):
+        environment.PupperV3Env(**dict(common.env_kwargs(), path=tree))

@@ -183,3 +183,27 @@ def test_domain_randomize_shapes_and_ranges():
     assert len(np.unique(f[:, 0])) == 10
     sv2, _ = dr.domain_randomize(s, keys)
     np.testing.assert_array_equal(sv2.body_mass, sv.body_mass)
+
+
+def test_external_randoms_reproduce_the_key_tree():
+    """PupperRand rows (include/pupper_env.h): fed the raw uniforms the reference's key tree draws in one step
+    (environment.py:349-361, 499-523, 256-269, 291-293), the oracle's external-randoms mode reproduces the threefry step
+    bit for bit -- kicks, latency picks, observation noise, command / orientation resampling -- and leaves info["rng"] alone."""
+    env = common.make_env(resample_velocity_step=3, zero_command_probability=0.3, kick_probability=0.5)
+    n = 24
+    A = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    B = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    keys = common.env_keys(n)
+    A.reset(keys); B.reset(keys)
+    kicked = resampled = 0
+    for t in range(8):
+        a = common.actions(n, t)
+        ext = common.ext_rand_from_step_keys(A.envs["rng"])
+        B.envs = A.envs.copy()
+        before = A.envs["rng"].copy(); cmd0 = A.envs["command"].copy()
+        A.step(a); B.step(a, ext_rand=ext)
+        for f in ("qpos", "qvel", "obs", "reward", "done", "kick", "command", "desired_world_z", "action_buffer", "imu_buffer", "metrics"):
+            assert np.array_equal(A.envs[f], B.envs[f]), (t, f)
+        assert np.array_equal(B.envs["rng"], before)
+        kicked += int((A.envs["kick"] != 0).any(1).sum()); resampled += int((A.envs["command"] != cmd0).any(1).sum())
+    assert kicked > n and resampled > n
