@@ -126,6 +126,27 @@ def env_ranges(n: int, chunks: int, wave: int):
     return [(e0, min(size, n - e0)) for e0 in range(0, n, size)]
 
 
+def check_dr_contract(sys_v: System, nominal_body_ipos) -> None:
+    """The device DR table is the compact form of the reference's ``domain_randomize`` (domain_randomization.py:33-86): ONE
+    friction draw for every geom, ONE kp / kd for every actuator, a COM shift of the base body only.  A Brax
+    ``randomization_fn`` that varies more than that would be silently collapsed to it, so it is rejected instead."""
+    fr, gp, bp = np.asarray(sys_v.geom_friction), np.asarray(sys_v.actuator_gainprm), np.asarray(sys_v.actuator_biasprm)
+    if fr.ndim != 3 or gp.ndim != 3 or bp.ndim != 3:
+        raise PupperError("domain-randomised system: geom_friction, actuator_gainprm and actuator_biasprm must be batched [n_envs, ...]")
+    nominal = np.asarray(nominal_body_ipos, dtype=np.float64)
+    checks = (
+        (np.all(fr[:, :, 0] == fr[:, :1, 0]), "geom_friction[:, g, 0] differs between geoms of one env"),
+        (np.all(gp[:, :, 0] == gp[:, :1, 0]), "actuator_gainprm[:, a, 0] (kp) differs between actuators of one env"),
+        (np.all(bp[:, :, 2] == bp[:, :1, 2]), "actuator_biasprm[:, a, 2] (-kd) differs between actuators of one env"),
+        (np.all(bp[:, :, 1] == -gp[:, :, 0]), "actuator_biasprm[:, a, 1] is not -kp (position actuators need biasprm[1] = -gainprm[0])"),
+        (np.allclose(np.asarray(sys_v.body_ipos)[:, 2:], nominal[None, 2:], rtol=0, atol=1e-7),
+         "body_ipos of a leg body differs from the model's (only the base COM is randomised)"),
+    )
+    for ok, what in checks:
+        if not ok:
+            raise PupperError(f"domain-randomised system is outside the supported DR contract: {what}")
+
+
 class EnvRuntime:
     def __init__(self, model_desc: abi.PupperModelDesc, env_cfg: abi.PupperEnvCfg, n_envs: int, device: int = 0,
                  episode: bool = False, debug: bool = False, guard_rows: int = 0):
@@ -136,6 +157,7 @@ class EnvRuntime:
         self.device = torch.device("cuda", device)
         self.device_index = device
         self.cfg = env_cfg
+        self._nominal_body_ipos = np.ctypeslib.as_array(model_desc.body_ipos).copy()  # [14, 3] (set_dr checks leg COMs against it)
         self.stride = (self.n_envs + 31) // 32 * 32
         self._model = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -219,6 +241,7 @@ class EnvRuntime:
         B = sys_v.body_mass.shape[0]
         if B != self.n_envs:
             raise PupperError(f"domain-randomised system has {B} envs, runtime has {self.n_envs}")
+        check_dr_contract(sys_v, self._nominal_body_ipos)
         host = {
             "friction": sys_v.geom_friction[:, 0, 0][None],
             "kp": sys_v.actuator_gainprm[:, 0, 0][None],
@@ -329,6 +352,16 @@ class EnvRuntime:
         w = self.cfg.observation_history * abi.OBS_DIM
         if h_action.dtype != torch.float32 or h_action.numel() != n * abi.NU or h_out.dtype != torch.float32 or h_out.numel() != n * (w + 2):
             raise PupperError("h_action must be float32 [n_envs, 12] and h_out float32 [n_envs * (H*36 + 2)]")
+        ok = getattr(self, "_host_ok", None)
+        if ok is None:
+            ok = self._host_ok = set()
+        for name, t in (("h_action", h_action), ("h_out", h_out)):
+            if (t.data_ptr(), t.numel()) in ok:
+                continue  # validated on an earlier call (is_pinned() asks the driver)
+            if t.device.type != "cpu" or not t.is_contiguous() or not t.is_pinned():
+                raise PupperError(f"{name} must be a contiguous, pinned host tensor (a pageable buffer turns the asynchronous copies "
+                                  "synchronous and serialises the three-stream pipeline)")
+            ok.add((t.data_ptr(), t.numel()))
         if chunks is None:
             chunks = max(1, min(8, n // 16384))
         if not hasattr(self, "_d_act"):
@@ -350,7 +383,7 @@ class EnvRuntime:
             if rc != 0:
                 _check(self.lib, rc, "pupper_step")
             self.launches += 1
-            h_out.copy_(self._out_pack, non_blocking=True)
+            h_out.view(-1).copy_(self._out_pack, non_blocking=True)
             return cur
         done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
         ha, flat = h_action.view(n, abi.NU), h_out.view(-1)

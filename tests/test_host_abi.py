@@ -15,10 +15,10 @@ HEADER = os.path.join(common.ROOT, "include", "pupper_env.h")
 
 def test_library_exports_every_declared_symbol():
     lib = runtime.load_library()
-    text = open(HEADER).read() + open(os.path.join(common.ROOT, "include", "pupper_policy.h")).read()
+    text = "".join(open(os.path.join(common.ROOT, "include", h)).read() for h in ("pupper_env.h", "pupper_policy.h", "pupper_ffi.h"))
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(pupper_[a-z_]+)\s*\(", text)
-    assert len(set(names)) >= 12 and "pupper_policy_forward" in names
+    names = re.findall(r"\b(pupper_[a-z_]+|Pupper[A-Za-z]+Ffi)\s*\(", text)
+    assert len(set(names)) >= 25 and "pupper_policy_forward" in names and "PupperStepFfi" in names and "pupper_state_blob_bind" in names
     for name in set(names):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
 
@@ -181,3 +181,22 @@ def test_contact_caps_outside_the_kernel_range_are_rejected_with_a_clear_message
             custom.remove(el)
     with pytest.raises(mjcf.UnsupportedModelError, match="no limit"):
         environment.PupperV3Env(**dict(common.env_kwargs(), path=tree))
+
+
+def test_dr_contract_check_rejects_what_the_device_table_cannot_hold():
+    """runtime.check_dr_contract: the reference's domain_randomize passes; per-geom friction, per-actuator gains, kp/bias
+    mismatch and leg COM shifts are refused instead of being silently collapsed."""
+    from pupperv3_mjx_b200 import domain_randomization as dr, prng
+    env = common.make_env()
+    nominal = np.ctypeslib.as_array(env.model_desc.body_ipos).copy()
+    sys_v, _ = dr.domain_randomize(env.sys, prng.split(prng.PRNGKey(2), 8))
+    runtime.check_dr_contract(sys_v, nominal)
+    def tweak(field, idx, delta):
+        a = np.array(getattr(sys_v, field), copy=True)
+        a[idx] += delta
+        return sys_v.replace(**{field: a}) if hasattr(sys_v, "replace") else sys_v.tree_replace({field: a})
+    for field, idx, what in (("geom_friction", (0, 3, 0), "geom_friction"), ("actuator_gainprm", (1, 2, 0), "kp"),
+                             ("actuator_biasprm", (2, 5, 2), "kd"), ("actuator_biasprm", (3, slice(None), 1), "not -kp"),
+                             ("body_ipos", (4, 5, 0), "leg body")):
+        with pytest.raises(runtime.PupperError, match=what):
+            runtime.check_dr_contract(tweak(field, idx, 0.125), nominal)
