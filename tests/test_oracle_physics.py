@@ -206,3 +206,97 @@ def test_obstacle_contacts_appear_and_push_up():
             top = (sel & (d["contact_frame"][:, :5, 0, 2] < -0.9)).any(1)
             assert np.all(d["qfrc_constraint"][:, 2][top] > 0)
     assert seen > 20
+
+
+def test_set_const_matches_an_independent_derivation():
+    """`mjcf.set_const` (numpy: M0 as a sum of J^T [m, I] J over bodies, explicit inverse, point
+    Jacobians) against the same constants derived from the C oracle's own quantities at qpos0 -- CRBA mass matrix,
+    spatial cdof columns about the subtree COM -- and against unit-force responses: dof_invweight0[i] is what a unit
+    generalized force on dof i accelerates dof i by (A = M0^-1), measured here as the change of qacc_smooth per unit of
+    actuator force between two oracle runs that differ in one motor target only."""
+    env = common.make_env(environment_timestep=0.004, latency_distribution=[1.0], **QUIET)  # one substep: taps = forward at the injected state
+    m = env._model
+    n = 13
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    O.reset(common.env_keys(n))
+    e = O.envs
+    e["qpos"][:] = m.qpos0[None]
+    e["qpos"][:, 2] = 1.0  # clear of the floor: the constants do not depend on the base position
+    e["qvel"][:] = 0; e["qacc_warmstart"][:] = 0
+    a = np.zeros((n, 12))
+    for i in range(12):
+        a[1 + i, i] = 0.05  # env 1+i: motor target of joint i moved by 0.05 * action_scale
+    O.step(a, debug=True)
+    d = O.debug
+    M0 = d["qM"][0]
+    A = np.linalg.inv(M0)
+    np.testing.assert_allclose(M0, m.M0, rtol=0, atol=2e-7)  # the oracle works from the float32 copies of the model constants
+    assert abs(np.mean(np.diag(M0)) - m.meaninertia) < 1e-7
+    inv = np.diag(A).copy(); inv[:3] = inv[:3].mean(); inv[3:6] = inv[3:6].mean()
+    np.testing.assert_allclose(inv, m.dof_invweight0, rtol=1e-5)
+    # unit-force responses through the oracle's own solve (CRBA + Cholesky), hinge dofs
+    for i in range(12):
+        df = d["qfrc_actuator"][1 + i] - d["qfrc_actuator"][0]
+        assert abs(df[6 + i]) > 1e-3 and np.abs(np.delete(df, 6 + i)).max() == 0
+        resp = (d["qacc_smooth"][1 + i][6 + i] - d["qacc_smooth"][0][6 + i]) / df[6 + i]
+        assert abs(resp - m.dof_invweight0[6 + i]) <= 1e-5 * m.dof_invweight0[6 + i], (i, resp, m.dof_invweight0[6 + i])
+    # body_invweight0 (translational part; the only one contacts use) from the oracle's spatial quantities
+    cdof, C, xipos = d["cdof"][0], d["subtree_com"][0], d["xipos"][0]
+    for b in range(1, 14):
+        J = np.zeros((3, 18))
+        chain = list(range(6))
+        if b >= 2:
+            leg, depth = divmod(b - 2, 3)
+            chain += [6 + 3 * leg + j for j in range(depth + 1)]
+        for k in chain:
+            J[:, k] = cdof[k][3:] + np.cross(cdof[k][:3], xipos[b] - C)
+        tr = np.trace(J @ A @ J.T) / 3.0
+        assert abs(tr - m.body_invweight0[b, 0]) <= 1e-5 * tr, (b, tr, m.body_invweight0[b, 0])
+
+
+def test_impedance_curve_matches_the_documented_closed_form():
+    """MuJoCo's documented constraint impedance (solimp = dmin, dmax, width, midpoint, power) and reference acceleration
+    (solref = timeconst, dampratio), evaluated by hand for five penetrations of the floor contact
+    (solimp 0.4575 0.975 0.016 0.5 2, solref 0.02 1): x = |pos| / width; power 2, midpoint 0.5: y = 2 x^2 for x < 0.5,
+    1 - 2 (1 - x)^2 above; d = dmin + y (dmax - dmin), d = dmax for x >= 1; b = 2 / (dmax tc), k = 1 / (dmax^2 tc^2 dr^2);
+    aref = -b v - k d pos; R = max(mjMINVAL, invweight (1 - d) / d), efc_D = 1 / R.  The oracle's contact rows must carry
+    exactly these numbers (it is the restatement the CUDA path is tested against)."""
+    env = common.make_env(environment_timestep=0.004, latency_distribution=[1.0], **QUIET)
+    m = env._model
+    depths = np.array([0.0004, 0.004, 0.008, 0.012, 0.02])  # x = 0.025, 0.25, 0.5, 0.75, 1.25
+    expect_d = [0.4575 + 2 * 0.025 ** 2 * 0.5175, 0.4575 + 2 * 0.25 ** 2 * 0.5175, 0.4575 + 0.5 * 0.5175,
+                0.4575 + (1 - 2 * 0.25 ** 2) * 0.5175, 0.975]
+    n = len(depths)
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    O.reset(common.env_keys(n))
+    e = O.envs
+    e["qpos"][:] = m.qpos0[None]
+    e["qvel"][:] = 0; e["qacc_warmstart"][:] = 0
+    O.envs = e
+    # find the base height that puts the lowest foot sphere `depth` into the floor: one probe step, then shift
+    probe = e.copy()
+    probe["qpos"][:, 2] = 1.0
+    O.envs = probe.copy()
+    O.step(np.zeros((n, 12)), debug=True)
+    sph_z = O.debug["sphere_xpos"][0][:, 2]
+    radius = np.ctypeslib.as_array(env.model_desc.sphere_radius)
+    low = int(np.argmin(sph_z - radius))
+    e["qpos"][:, 2] = 1.0 - (sph_z[low] - radius[low]) - depths
+    O.envs = e.copy()
+    O.step(np.zeros((n, 12)), debug=True)
+    d = O.debug
+    tc, dmax = 0.02, 0.975
+    b_gain, k_gain = 2.0 / (dmax * tc), 1.0 / (dmax * dmax * tc * tc)
+    mu = 1.0
+    for i in range(n):
+        c = int(np.argmin(np.abs(d["contact_dist"][i][:d["ncon"][i]] + depths[i])))
+        assert abs(d["contact_dist"][i][c] + depths[i]) < 1e-6
+        body = 2 + 3 * (low // 2) + 1 + (low % 2)  # link2 (knee sphere) or link3 (foot sphere) of that leg
+        t = m.body_invweight0[body, 0]
+        invw = (t + mu * mu * t) * 2 * mu * mu / float(env.model_desc.impratio)
+        R = max(1e-15, invw * (1 - expect_d[i]) / expect_d[i])
+        row = 24 + 4 * c
+        np.testing.assert_allclose(d["efc_D"][i][row:row + 4], 1.0 / R, rtol=1e-5)
+        # zero velocity: aref = -k d pos, identical on the four pyramid edges
+        np.testing.assert_allclose(d["efc_aref"][i][row:row + 4], k_gain * expect_d[i] * depths[i], rtol=1e-5)
+    assert abs(b_gain - 2.0 / (0.975 * 0.02)) < 1e-12
