@@ -119,7 +119,20 @@ __device__ __forceinline__ float qsum(float v, unsigned qm) {
   return v;
 }
 __device__ __forceinline__ V3 qsum3(V3 v, unsigned qm) { return V3{qsum(v.x, qm), qsum(v.y, qm), qsum(v.z, qm)}; }
+#if PUPPER_F2
+__device__ __forceinline__ S6 qsum6(S6 v, unsigned qm) {  // same sums, the additions on register pairs
+  P6 p = pack6(v);
+#pragma unroll
+  for (int sft = 1; sft <= 2; sft <<= 1) {
+    p.p0 = __fadd2_rn(p.p0, make_float2(__shfl_xor_sync(qm, p.p0.x, sft), __shfl_xor_sync(qm, p.p0.y, sft)));
+    p.p1 = __fadd2_rn(p.p1, make_float2(__shfl_xor_sync(qm, p.p1.x, sft), __shfl_xor_sync(qm, p.p1.y, sft)));
+    p.p2 = __fadd2_rn(p.p2, make_float2(__shfl_xor_sync(qm, p.p2.x, sft), __shfl_xor_sync(qm, p.p2.y, sft)));
+  }
+  return unpack6(p);
+}
+#else
 __device__ __forceinline__ S6 qsum6(S6 v, unsigned qm) { return S6{qsum3(v.a, qm), qsum3(v.l, qm)}; }
+#endif
 __device__ __forceinline__ float qbcast(float v, int src, unsigned qm, int qbase) { return __shfl_sync(qm, v, qbase + src); }
 
 // Arrow-structured symmetric matrix over (base 6 | leg 3), one leg per lane.
@@ -130,8 +143,49 @@ struct TreeMat {
 };
 __device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
+#if PUPPER_F2
+// Packed FP32x2 views of a 6-row (three register pairs) with a broadcast scalar: r = s * a (+ b), element-wise IEEE.
+struct R6 { float2 p0, p1, p2; };
+__device__ __forceinline__ R6 row6(const float a[6]) { return R6{make_float2(a[0], a[1]), make_float2(a[2], a[3]), make_float2(a[4], a[5])}; }
+__device__ __forceinline__ void unrow6(R6 r, float a[6]) { a[0] = r.p0.x; a[1] = r.p0.y; a[2] = r.p1.x; a[3] = r.p1.y; a[4] = r.p2.x; a[5] = r.p2.y; }
+__device__ __forceinline__ R6 mul6(float s, R6 a) { const float2 ss = make_float2(s, s); return R6{__fmul2_rn(ss, a.p0), __fmul2_rn(ss, a.p1), __fmul2_rn(ss, a.p2)}; }
+__device__ __forceinline__ R6 fmar6(float s, R6 a, R6 b) {
+  const float2 ss = make_float2(s, s);
+  return R6{__ffma2_rn(ss, a.p0, b.p0), __ffma2_rn(ss, a.p1, b.p1), __ffma2_rn(ss, a.p2, b.p2)};
+}
+__device__ __forceinline__ float dotr6(R6 a, R6 b) {
+  const float2 t = __ffma2_rn(a.p2, b.p2, __ffma2_rn(a.p1, b.p1, __fmul2_rn(a.p0, b.p0)));
+  return t.x + t.y;
+}
+__device__ __forceinline__ float2 qsum2(float2 v, unsigned qm) {
+  v = __fadd2_rn(v, make_float2(__shfl_xor_sync(qm, v.x, 1), __shfl_xor_sync(qm, v.y, 1)));
+  return __fadd2_rn(v, make_float2(__shfl_xor_sync(qm, v.x, 2), __shfl_xor_sync(qm, v.y, 2)));
+}
+#endif
+
 // y = A x for the arrow matrix (A.B must already hold the full base block)
 __device__ __forceinline__ void tree_matvec(const TreeMat &A, const float xb[6], const float xl[3], float yb[6], float yl[3], unsigned qm) {
+#if PUPPER_F2
+  const R6 X = row6(xb), C0 = row6(A.C[0]), C1 = row6(A.C[1]), C2 = row6(A.C[2]);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float s = dotr6(j == 0 ? C0 : (j == 1 ? C1 : C2), X);
+#pragma unroll
+    for (int i = 0; i < 3; i++) s = fmaf(A.D[i >= j ? tri(i, j) : tri(j, i)], xl[i], s);
+    yl[j] = s;
+  }
+  R6 t = fmar6(xl[2], C2, fmar6(xl[1], C1, mul6(xl[0], C0)));
+  t = R6{qsum2(t.p0, qm), qsum2(t.p1, qm), qsum2(t.p2, qm)};
+  float tb[6];
+  unrow6(t, tb);
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float s = tb[d];
+#pragma unroll
+    for (int i = 0; i < 6; i++) s = fmaf(A.B[i >= d ? tri(i, d) : tri(d, i)], xb[i], s);
+    yb[d] = s;
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     float s = 0.f;
@@ -151,11 +205,38 @@ __device__ __forceinline__ void tree_matvec(const TreeMat &A, const float xb[6],
     for (int i = 0; i < 6; i++) s = fmaf(A.B[i >= d ? tri(i, d) : tri(d, i)], xb[i], s);
     yb[d] = s;
   }
+#endif
 }
 
 // Same product with the matrix read from shared memory (layout: element i of [B(21) | C(18) | D(6)] at sm[i*kBlock])
 __device__ __forceinline__ void tree_matvec_smem(const float *sm, const float xb[6], const float xl[3], float yb[6], float yl[3], unsigned qm) {
   const float *B = sm, *C = sm + 21 * kBlock, *D = sm + 39 * kBlock;
+#if PUPPER_F2
+  float c[3][6];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int d = 0; d < 6; d++) c[j][d] = C[(j * 6 + d) * kBlock];
+  const R6 X = row6(xb), C0 = row6(c[0]), C1 = row6(c[1]), C2 = row6(c[2]);
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    float s = dotr6(j == 0 ? C0 : (j == 1 ? C1 : C2), X);
+#pragma unroll
+    for (int i = 0; i < 3; i++) s = fmaf(D[(i >= j ? tri(i, j) : tri(j, i)) * kBlock], xl[i], s);
+    yl[j] = s;
+  }
+  R6 t = fmar6(xl[2], C2, fmar6(xl[1], C1, mul6(xl[0], C0)));
+  t = R6{qsum2(t.p0, qm), qsum2(t.p1, qm), qsum2(t.p2, qm)};
+  float tb[6];
+  unrow6(t, tb);
+#pragma unroll
+  for (int d = 0; d < 6; d++) {
+    float s = tb[d];
+#pragma unroll
+    for (int i = 0; i < 6; i++) s = fmaf(B[(i >= d ? tri(i, d) : tri(d, i)) * kBlock], xb[i], s);
+    yb[d] = s;
+  }
+#else
 #pragma unroll
   for (int j = 0; j < 3; j++) {
     float s = 0.f;
@@ -175,6 +256,7 @@ __device__ __forceinline__ void tree_matvec_smem(const float *sm, const float xb
     for (int i = 0; i < 6; i++) s = fmaf(B[(i >= d ? tri(i, d) : tri(d, i)) * kBlock], xb[i], s);
     yb[d] = s;
   }
+#endif
 }
 
 // In-place leaves-first Cholesky.  On exit: D = L_k (3x3 lower), C = Y_k = L_k^-1 C_k,
@@ -187,6 +269,33 @@ __device__ __forceinline__ void tree_factor(TreeMat &A, const float *Badd, unsig
   float l21 = (A.D[4] - l20 * l10) * i11;
   float i22 = rsqrtf(A.D[5] - l20 * l20 - l21 * l21);
   A.D[0] = i00; A.D[1] = l10; A.D[2] = i11; A.D[3] = l20; A.D[4] = l21; A.D[5] = i22;  // diagonals hold 1 / l_ii
+#if PUPPER_F2
+  const R6 Y0 = mul6(i00, row6(A.C[0]));
+  const R6 Y1 = mul6(i11, fmar6(-l10, Y0, row6(A.C[1])));
+  const R6 Y2 = mul6(i22, fmar6(-l21, Y1, fmar6(-l20, Y0, row6(A.C[2]))));
+  unrow6(Y0, A.C[0]); unrow6(Y1, A.C[1]); unrow6(Y2, A.C[2]);
+  // Schur complement, row i of the lower triangle as register pairs (j, j+1); the half of a pair beyond the diagonal is unused
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float n0 = -A.C[0][i], n1 = -A.C[1][i], n2 = -A.C[2][i];
+#pragma unroll
+    for (int jp = 0; jp <= i; jp += 2) {
+      const bool both = jp + 1 <= i;
+      float2 s = Badd ? make_float2(Badd[tri(i, jp)], both ? Badd[tri(i, jp + 1)] : 0.f) : make_float2(0.f, 0.f);
+      const float2 y0 = jp == 0 ? Y0.p0 : (jp == 2 ? Y0.p1 : Y0.p2), y1 = jp == 0 ? Y1.p0 : (jp == 2 ? Y1.p1 : Y1.p2),
+                   y2 = jp == 0 ? Y2.p0 : (jp == 2 ? Y2.p1 : Y2.p2);
+      s = __ffma2_rn(make_float2(n0, n0), y0, s);
+      s = __ffma2_rn(make_float2(n1, n1), y1, s);
+      s = __ffma2_rn(make_float2(n2, n2), y2, s);
+      if (both) {
+        s = qsum2(s, qm);
+        A.B[tri(i, jp)] += s.x; A.B[tri(i, jp + 1)] += s.y;
+      } else {
+        A.B[tri(i, jp)] += qsum(s.x, qm);
+      }
+    }
+  }
+#else
 #pragma unroll
   for (int d = 0; d < 6; d++) {
     float y0 = A.C[0][d] * i00;
@@ -204,6 +313,7 @@ __device__ __forceinline__ void tree_factor(TreeMat &A, const float *Badd, unsig
       s = fmaf(-A.C[2][i], A.C[2][j], s);
       A.B[tri(i, j)] += qsum(s, qm);
     }
+#endif
 #pragma unroll
   for (int i = 0; i < 6; i++)
 #pragma unroll
@@ -221,11 +331,22 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
   float z1 = (gl[1] - F.D[1] * z0) * F.D[2];
   float z2 = (gl[2] - F.D[3] * z0 - F.D[4] * z1) * F.D[5];
   float y[6];
+#if PUPPER_F2
+  const R6 C0 = row6(F.C[0]), C1 = row6(F.C[1]), C2 = row6(F.C[2]);
+  {
+    R6 t = fmar6(z0, C0, fmar6(z1, C1, mul6(z2, C2)));
+    t = R6{qsum2(t.p0, qm), qsum2(t.p1, qm), qsum2(t.p2, qm)};
+    const R6 G = row6(gb);
+    unrow6(R6{__fadd2_rn(G.p0, make_float2(-t.p0.x, -t.p0.y)), __fadd2_rn(G.p1, make_float2(-t.p1.x, -t.p1.y)),
+              __fadd2_rn(G.p2, make_float2(-t.p2.x, -t.p2.y))}, y);
+  }
+#else
 #pragma unroll
   for (int d = 0; d < 6; d++) {
     float s = fmaf(F.C[0][d], z0, fmaf(F.C[1][d], z1, F.C[2][d] * z2));
     y[d] = gb[d] - qsum(s, qm);
   }
+#endif
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     float s = y[i];
@@ -240,6 +361,10 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
     for (int p = i + 1; p < 6; p++) s = fmaf(-F.B[tri(p, i)], xb[p], s);
     xb[i] = s * F.B[tri(i, i)];
   }
+#if PUPPER_F2
+  const R6 X = row6(xb);
+  const float w0 = z0 - dotr6(C0, X), w1 = z1 - dotr6(C1, X), w2 = z2 - dotr6(C2, X);
+#else
   float w0 = z0, w1 = z1, w2 = z2;
 #pragma unroll
   for (int d = 0; d < 6; d++) {
@@ -247,6 +372,7 @@ __device__ __forceinline__ void tree_solve(const TreeMat &F, const float gb[6], 
     w1 = fmaf(-F.C[1][d], xb[d], w1);
     w2 = fmaf(-F.C[2][d], xb[d], w2);
   }
+#endif
   xl[2] = w2 * F.D[5];
   xl[1] = (w1 - F.D[4] * xl[2]) * F.D[2];
   xl[0] = (w0 - F.D[1] * xl[1] - F.D[3] * xl[2]) * F.D[0];
@@ -1280,10 +1406,54 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
             Jc[d][0] = s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z;
             Jc[d][1] = s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z;
             Jc[d][2] = s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z;
+#if !PUPPER_F2
+            T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
+            T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
+            T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
+#endif
+          }
+#if PUPPER_F2
+          // The same products on register pairs: the base part of each contact-frame row of Jc (dofs 0-5) is three pairs,
+          // every update is "broadcast scalar x pair + pair" (FFMA2), so the block costs about two thirds of the scalar form.
+          float2 J0[3], J1[3], J2[3], T0[3], T1[3], T2[3];  // rows normal / tangent 1 / tangent 2, pairs (0,1) (2,3) (4,5)
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            J0[q] = make_float2(Jc[2 * q][0], Jc[2 * q + 1][0]);
+            J1[q] = make_float2(Jc[2 * q][1], Jc[2 * q + 1][1]);
+            J2[q] = make_float2(Jc[2 * q][2], Jc[2 * q + 1][2]);
+            T0[q] = __ffma2_rn(make_float2(W02, W02), J2[q], __ffma2_rn(make_float2(W01, W01), J1[q], __fmul2_rn(make_float2(W00, W00), J0[q])));
+            T1[q] = __ffma2_rn(make_float2(W11, W11), J1[q], __fmul2_rn(make_float2(W01, W01), J0[q]));
+            T2[q] = __ffma2_rn(make_float2(W22, W22), J2[q], __fmul2_rn(make_float2(W02, W02), J0[q]));
+          }
+#pragma unroll
+          for (int d = 6; d < 9; d++) {
             T[d][0] = W00 * Jc[d][0] + W01 * Jc[d][1] + W02 * Jc[d][2];
             T[d][1] = W01 * Jc[d][0] + W11 * Jc[d][1];
             T[d][2] = W02 * Jc[d][0] + W22 * Jc[d][2];
           }
+#pragma unroll
+          for (int i2 = 0; i2 < 6; i2++) {
+            const float2 t0p = T0[i2 >> 1], t1p = T1[i2 >> 1], t2p = T2[i2 >> 1];
+            const float t0 = (i2 & 1) ? t0p.y : t0p.x, t1 = (i2 & 1) ? t1p.y : t1p.x, t2 = (i2 & 1) ? t2p.y : t2p.x;
+#pragma unroll
+            for (int jp = 0; jp <= i2; jp += 2) {
+              const float2 v = __ffma2_rn(make_float2(t2, t2), J2[jp >> 1], __ffma2_rn(make_float2(t1, t1), J1[jp >> 1], __fmul2_rn(make_float2(t0, t0), J0[jp >> 1])));
+              Badd[tri(i2, jp)] += v.x;
+              if (jp + 1 <= i2) Badd[tri(i2, jp + 1)] += v.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            R6 c = row6(H.C[j]);
+            const float2 a0 = make_float2(T[6 + j][0], T[6 + j][0]), a1 = make_float2(T[6 + j][1], T[6 + j][1]), a2 = make_float2(T[6 + j][2], T[6 + j][2]);
+            c.p0 = __ffma2_rn(a2, J2[0], __ffma2_rn(a1, J1[0], __ffma2_rn(a0, J0[0], c.p0)));
+            c.p1 = __ffma2_rn(a2, J2[1], __ffma2_rn(a1, J1[1], __ffma2_rn(a0, J0[1], c.p1)));
+            c.p2 = __ffma2_rn(a2, J2[2], __ffma2_rn(a1, J1[2], __ffma2_rn(a0, J0[2], c.p2)));
+            unrow6(c, H.C[j]);
+#pragma unroll
+            for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
+          }
+#else
 #pragma unroll
           for (int i2 = 0; i2 < 6; i2++)
 #pragma unroll
@@ -1295,6 +1465,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
             for (int jj = 0; jj <= j; jj++) H.D[tri(j, jj)] += T[6 + j][0] * Jc[6 + jj][0] + T[6 + j][1] * Jc[6 + jj][1] + T[6 + j][2] * Jc[6 + jj][2];
           }
+#endif
         }
       }
     }

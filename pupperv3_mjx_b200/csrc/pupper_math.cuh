@@ -17,24 +17,48 @@ struct S6 {  // spatial vector: angular a, linear l
   V3 a, l;
 };
 
+#ifndef PUPPER_F2
+#define PUPPER_F2 1  // packed FP32x2 (FFMA2 / FADD2 / FMUL2, sm_100) for 6-vector arithmetic: same IEEE results per element, half the
+#endif               // instructions to fetch -- the step kernel is instruction-fetch bound in its straight-line phases
+#ifndef PUPPER_F2_V3
+#define PUPPER_F2_V3 0  // ... and for the (x, y) halves of 3-vector sums / scalings: the register pairing costs more MOVs than it saves (static count +48)
+#endif
 __device__ __forceinline__ V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+#if PUPPER_F2_V3
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) {
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return V3{r.x, r.y, a.z + b.z};
+}
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) {
+  const float2 r = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+  return V3{r.x, r.y, a.z - b.z};
+}
+__device__ __forceinline__ V3 operator*(float s, V3 a) {
+  const float2 r = __fmul2_rn(make_float2(s, s), make_float2(a.x, a.y));
+  return V3{r.x, r.y, s * a.z};
+}
+__device__ __forceinline__ V3 operator*(V3 a, float s) { return s * a; }
+#else
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ V3 operator*(float s, V3 a) { return V3{s * a.x, s * a.y, s * a.z}; }
 __device__ __forceinline__ V3 operator*(V3 a, float s) { return V3{s * a.x, s * a.y, s * a.z}; }
+#endif
+__device__ __forceinline__ V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) {
   return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 __device__ __forceinline__ V3 fma3(float s, V3 a, V3 b) {  // s*a + b
+#if PUPPER_F2_V3
+  const float2 r = __ffma2_rn(make_float2(s, s), make_float2(a.x, a.y), make_float2(b.x, b.y));
+  return V3{r.x, r.y, fmaf(s, a.z, b.z)};
+#else
   return V3{fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z)};
+#endif
 }
 __device__ __forceinline__ float comp(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
-#ifndef PUPPER_F2
-#define PUPPER_F2 1  // packed FP32x2 (FFMA2 / FADD2 / FMUL2, sm_100) for 6-vector arithmetic: same IEEE results per element, half the
-#endif               // instructions to fetch -- the step kernel is instruction-fetch bound in its straight-line phases
 #if PUPPER_F2
 // a 6-vector as three register pairs: (a.x, a.y) (a.z, l.x) (l.y, l.z)
 struct P6 { float2 p0, p1, p2; };
@@ -59,7 +83,15 @@ __device__ __forceinline__ S6 operator+(S6 a, S6 b) { return S6{a.a + b.a, a.l +
 __device__ __forceinline__ S6 operator*(float s, S6 a) { return S6{s * a.a, s * a.l}; }
 __device__ __forceinline__ S6 fma6(float s, S6 a, S6 b) { return S6{fma3(s, a.a, b.a), fma3(s, a.l, b.l)}; }
 #endif
+#if PUPPER_F2
+__device__ __forceinline__ float dot6(S6 a, S6 b) {
+  const P6 x = pack6(a), y = pack6(b);
+  const float2 t = __ffma2_rn(x.p2, y.p2, __ffma2_rn(x.p1, y.p1, __fmul2_rn(x.p0, y.p0)));
+  return t.x + t.y;
+}
+#else
 __device__ __forceinline__ float dot6(S6 a, S6 b) { return dot(a.a, b.a) + dot(a.l, b.l); }
+#endif
 // motion cross product u x v  = [u.a x v.a, u.l x v.a + u.a x v.l]
 __device__ __forceinline__ S6 motion_cross(S6 u, S6 v) { return S6{cross(u.a, v.a), cross(u.l, v.a) + cross(u.a, v.l)}; }
 // force cross product v x* f = [v.a x f.a + v.l x f.l, v.a x f.l]
