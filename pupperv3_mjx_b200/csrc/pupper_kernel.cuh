@@ -747,6 +747,353 @@ __device__ __noinline__ void dense_newton_direction(const EnvShared &es, int nco
     }
 }
 
+// efc_D and aref of a joint-limit row at violation p < 0 (rare; out of line)
+__device__ __noinline__ float2 limit_row(const float *solref, const float *solimp, float dt, float p, float signed_vel, float invweight) {
+  float kk, bb, imp;
+  kbi(solref, solimp, dt, p, kk, bb, imp);
+  return make_float2(1.f / fmaxf(invweight * (1.f - imp) / imp, kMinVal), -bb * signed_vel - kk * imp * p);
+}
+
+// Memory-backed arguments of the out-of-line leg-leg row evaluation (N generalized vectors)
+template <int N>
+struct LegLegIO {
+  S6 cd[3];
+  V3 ba[3], bo[3];
+  float vb[N][6], vl[N][3];
+};
+__device__ __noinline__ void legleg_rows3(const EnvShared &es, const LegLegIO<3> &io, float esgn, bool et2, int part_all, int slots, int slots_w, float *out) {
+  contact_rows_legleg<3>(es, io.cd, io.ba, io.bo, io.vb, io.vl, esgn, et2, 0xffffffffu, part_all, slots, slots_w, out);
+}
+__device__ __noinline__ void legleg_rows1(const EnvShared &es, const LegLegIO<1> &io, float esgn, bool et2, int part_all, int slots, int slots_w, float *out) {
+  contact_rows_legleg<1>(es, io.cd, io.ba, io.bo, io.vb, io.vl, esgn, et2, 0xffffffffu, part_all, slots, slots_w, out);
+}
+// Leg-leg slots hold raw rows (J.qvel in buffer A, J.warmstart in B, J.qacc_smooth in C of this lane's column `rowA`):
+// turns B and C into Jaref and returns this lane's cost at both start points.
+__device__ __noinline__ float2 legleg_start_cost(const EnvShared &es, int ss_mask, float *rowA) {
+  float *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
+  float cw = 0.f, cs = 0.f;
+#pragma unroll 1
+  for (int rem = ss_mask; rem; rem &= rem - 1) {
+    const int c = __ffs(rem) - 1;
+    const ContactSlot &s = es.con[c];
+    float aref = -s.b * rowA[c * kBlock] - s.kimp;
+    float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
+    rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;
+    const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
+    cw = fmaf(0.5f * s.D * mw, mw, cw);
+    cs = fmaf(0.5f * s.D * ms, ms, cs);
+  }
+  return make_float2(cw, cs);
+}
+// Wrenches of the leg-leg contacts on this leg's link2 / link3 chains (io[0], io[1]); `ja0` points at edge 0 of slot 0 of
+// the chosen start's Jaref buffer as seen from the quad.
+__device__ __noinline__ void legleg_wrench(const EnvShared &es, int ss_mask, const float *ja0, int part_all, S6 (&io)[2]) {
+  S6 S1 = io[0], S2 = io[1];
+#pragma unroll 1
+  for (int rem = ss_mask; rem; rem &= rem - 1) {
+    const int c = __ffs(rem) - 1;
+    const ContactSlot &s = es.con[c];
+    const float *ja = ja0 + c * kBlock;
+    const float D = s.D, mu = s.mu;
+    const float f0 = -D * fminf(ja[0], 0.f), f1 = -D * fminf(ja[1], 0.f), f2 = -D * fminf(ja[2], 0.f), f3 = -D * fminf(ja[3], 0.f);
+    const float Fn = (f0 + f1) + (f2 + f3), Ft1 = mu * (f0 - f1), Ft2 = mu * (f2 - f3);
+    const V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
+                    s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
+    const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+    const S6 w = S6{cross(r, g), g};
+    const int pc = (part_all >> (4 * c)) & 15;
+    const int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
+    const float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
+    S1 = fma6(s1w, w, S1);
+    S2 = fma6(s2w, w, S2);
+  }
+  io[0] = S1; io[1] = S2;
+}
+// This lane's view of the env's contact slots when they were not all plane contacts of its own spheres
+struct SlotScan {
+  int n_ss, css, ss_mask, part_all, own_list, own_count;
+  float knee_hits, torso_hits;
+};
+__device__ __noinline__ void scan_slots(uint32_t knee_mask, uint32_t torso_mask, const EnvShared &es, int ncon, int k, SlotScan &o) {
+  int n_ss = 0, css = 0, ss_mask = 0, part_all = 0, own_list = 0, own_count = 0;
+  float knee_hits = 0.f, torso_hits = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < ncon; c++) {
+    const ContactSlot &s = es.con[c];
+    const bool is_ss = (s.code1 >= 0 && s.code2 >= 0);
+    if (is_ss) { n_ss++; css = c; ss_mask |= 1 << c; }
+    {
+      const int pc = participation(s, k);
+      part_all |= pc << (4 * c);
+      if (pc && !is_ss) { own_list |= c << (3 * own_count); own_count++; }
+    }
+    if (s.s1 >= 0) { knee_hits += (float)((knee_mask >> s.s1) & 1u); torso_hits += (float)((torso_mask >> s.s1) & 1u); }
+    if (s.s2 >= 0) { knee_hits += (float)((knee_mask >> s.s2) & 1u); torso_hits += (float)((torso_mask >> s.s2) & 1u); }
+  }
+  o.n_ss = n_ss; o.css = css; o.ss_mask = ss_mask; o.part_all = part_all; o.own_list = own_list; o.own_count = own_count;
+  o.knee_hits = knee_hits; o.torso_hits = torso_hits;
+}
+
+// ---- collision candidates and the rare collision paths (out of line: see woodbury_direction) -------------------------
+struct Cand {  // one candidate contact of a lane
+  float dist;      // penetration (< 0) or kInf
+  V3 pos, n;       // world contact point, normal geom1 -> geom2
+  int code1, code2, s1, s2, box;
+};
+// raw candidate -> contact slot (the quad completes frame, friction and impedance afterwards); ty: 0 plane, 1 box, 2 leg-leg
+__device__ __forceinline__ void write_raw_slot(ContactSlot &s, const Cand &c, V3 C, int ty) {
+  s.r[0] = c.pos.x - C.x; s.r[1] = c.pos.y - C.y; s.r[2] = c.pos.z - C.z;
+  s.frame[0] = c.n.x; s.frame[1] = c.n.y; s.frame[2] = c.n.z;
+  s.dist = c.dist;
+  s.code1 = c.code1; s.code2 = c.code2; s.s1 = c.s1; s.s2 = c.s2; s.ty = ty; s.box = c.box;
+}
+
+// sphere-box: the broad phase keeps the max_geom_pairs pairs with the smallest bounding-sphere distance over all 8*nbox
+// pairs (pair index = sphere*nbox + box, ties to the lower index); the pair of rank i gets its narrow phase on lane i.
+// One pass per lane keeps its own 4 best pairs sorted, a 4-round merge over the quad ranks them, and the 4 narrow phases
+// then run side by side.  Called by the whole warp when the model has boxes.
+__device__ __noinline__ void box_candidate(const BlockShared &sh, const EnvShared &es, int k, int qbase, V3 sc0, V3 sc1, Cand &out) {
+  const PupperModelDesc &m = sh.m;
+  const unsigned qm = 0xffffffffu;
+  out.dist = kInf; out.pos = out.n = V3{0.f, 0.f, 0.f};
+  out.code1 = out.code2 = out.s1 = out.s2 = -1; out.box = 0;
+  const int nbox = m.nbox, maxp = m.max_geom_pairs;
+  float k0 = kInf, k1 = kInf, k2 = kInf, k3 = kInf;
+  int i0 = 0x7fffffff, i1 = 0x7fffffff, i2 = 0x7fffffff, i3 = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float rs = m.sphere_radius[2 * k + i];
+    const V3 sci = i == 0 ? sc0 : sc1;
+#pragma unroll 1
+    for (int bx = 0; bx < nbox; bx++) {
+      V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sci;
+      const float key = sqrtf(dot(d, d)) - (rs + sh.d.box_rbound[bx]);
+      const int id = (2 * k + i) * nbox + bx;  // ids grow along the pass, so strict '<' keeps ties in index order
+      const bool c0 = key < k0, c1 = key < k1, c2 = key < k2, c3 = key < k3;
+      k3 = c2 ? k2 : (c3 ? key : k3); i3 = c2 ? i2 : (c3 ? id : i3);
+      k2 = c1 ? k1 : (c2 ? key : k2); i2 = c1 ? i1 : (c2 ? id : i2);
+      k1 = c0 ? k0 : (c1 ? key : k1); i1 = c0 ? i0 : (c1 ? id : i1);
+      k0 = c0 ? key : k0; i0 = c0 ? id : i0;
+    }
+  }
+  const int nr = min(min(maxp, 4), 8 * nbox);
+  int mine = -1;
+#pragma unroll 1
+  for (int r = 0; r < nr; r++) {
+    float bk = k0;
+    int bi = i0;
+#pragma unroll
+    for (int sft = 1; sft <= 2; sft <<= 1) {
+      float ok = __shfl_xor_sync(qm, bk, sft);
+      int oi = __shfl_xor_sync(qm, bi, sft);
+      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    if (bi == i0) { k0 = k1; i0 = i1; k1 = k2; i1 = i2; k2 = k3; i2 = i3; k3 = kInf; i3 = 0x7fffffff; }  // this lane's head won: pop it
+    if (r == k) mine = bi;
+  }
+  if (mine >= 0) {  // narrow phase of the pair ranked k
+    const int sph = mine / nbox, bx = mine - sph * nbox;
+    V3 c = V3{es.sph[sph][0], es.sph[sph][1], es.sph[sph][2]};
+    V3 pp, nn;
+    float d = sphere_box(c, m.sphere_radius[sph], m.box_pos[bx], m.box_mat[bx], m.box_size[bx], pp, nn);
+    out.dist = d < 0.f ? d : kInf;
+    out.pos = pp; out.n = nn;
+    out.code1 = (sph >> 1) * 4 + 1 + (sph & 1); out.code2 = -1; out.s1 = sph; out.s2 = -1; out.box = bx;
+  }
+}
+
+// sphere-sphere (leg-leg): the max_geom_pairs closest of the 24 pairs, 6 per lane in MJX pair order; the pair of rank r
+// gets its narrow phase on lane r.  Called by the whole warp when some pair of the warp penetrates.
+__device__ __noinline__ void ss_candidate(const BlockShared &sh, const EnvShared &es, int k, int qbase, Cand &out) {
+  const PupperModelDesc &m = sh.m;
+  const unsigned qm = 0xffffffffu;
+  out.dist = kInf; out.pos = out.n = V3{0.f, 0.f, 0.f};
+  out.code1 = out.code2 = out.s1 = out.s2 = -1; out.box = 0;
+  const int maxp = m.max_geom_pairs;
+  float pd[6];
+  int pa[6], pb[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const int ab = sh.d.ss_pair[6 * k + i];
+    const int a = ab & 255, b = ab >> 8;
+    V3 d = V3{es.sph[b][0] - es.sph[a][0], es.sph[b][1] - es.sph[a][1], es.sph[b][2] - es.sph[a][2]};
+    pd[i] = sqrtf(dot(d, d)) - (m.sphere_radius[a] + m.sphere_radius[b]);
+    pa[i] = a; pb[i] = b;
+  }
+  uint32_t taken = 0u;
+  for (int r = 0; r < maxp && r < 24; r++) {
+    float bk = kInf;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+      if (!((taken >> i) & 1u) && (pd[i] < bk || (pd[i] == bk && 6 * k + i < bi))) { bk = pd[i]; bi = 6 * k + i; }
+#pragma unroll
+    for (int sft = 1; sft <= 2; sft <<= 1) {
+      float ok = __shfl_xor_sync(qm, bk, sft);
+      int oi = __shfl_xor_sync(qm, bi, sft);
+      if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
+    }
+    int owner = min(bi / 6, 3), li = bi - owner * 6;
+    int a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) if (i == li) { a = pa[i]; b = pb[i]; }
+    a = __shfl_sync(qm, a, qbase + owner);
+    b = __shfl_sync(qm, b, qbase + owner);
+    if (owner == k) taken |= 1u << li;
+    if ((r & 3) == k && r < 4 && bk < 0.f) {
+      V3 ca_ = V3{es.sph[a][0], es.sph[a][1], es.sph[a][2]}, cb_ = V3{es.sph[b][0], es.sph[b][1], es.sph[b][2]};
+      V3 n = cb_ - ca_;
+      float dn = normalize3(n);
+      if (dn == 0.f) n = V3{1.f, 0.f, 0.f};
+      float d = dn - (m.sphere_radius[a] + m.sphere_radius[b]);
+      out.dist = d < 0.f ? d : kInf;
+      out.n = n;
+      out.pos = ca_ + (m.sphere_radius[a] + d * 0.5f) * n;
+      out.code1 = (a >> 1) * 4 + 1 + (a & 1); out.code2 = (b >> 1) * 4 + 1 + (b & 1); out.s1 = a; out.s2 = b;
+    }
+  }
+}
+
+// The ranking cut: some env of the warp has more penetrating candidates than contact slots, so the max_contact_points
+// smallest distances over [plane 0..7, box 8..11, sphere-sphere 12..15] are kept, ties to the lower index.  Returns the
+// env's contact count; the winners' raw slots are written in rank order.  Called by the whole warp.
+struct CutIO { Cand c[4]; };
+__device__ __noinline__ int cut_candidates(EnvShared &es, int k, int qbase, int maxc, V3 C, CutIO &io) {
+  const unsigned qm = 0xffffffffu;
+  float cdist[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) cdist[i] = io.c[i].dist;
+  int ncon = 0;
+  for (int r = 0; r < maxc; r++) {
+    // local best of this lane's 4 candidates (ids grow with i, so the first minimum is also the lowest id)
+    const float bk = fminf(fminf(cdist[0], cdist[1]), fminf(cdist[2], cdist[3]));
+    const int bl = cdist[0] == bk ? 0 : (cdist[1] == bk ? 1 : (cdist[2] == bk ? 2 : 3));
+    const int bi = bk < kInf ? (bl < 2 ? 2 * k + bl : (bl == 2 ? 8 + k : 12 + k)) : 0x7fffffff;
+    float mk = bk;
+    int mi = bi;
+#pragma unroll
+    for (int sft = 1; sft <= 2; sft <<= 1) {
+      float ok = __shfl_xor_sync(qm, mk, sft);
+      int oi = __shfl_xor_sync(qm, mi, sft);
+      const bool take = (ok < mk) | ((ok == mk) & (oi < mi));
+      mk = take ? ok : mk; mi = take ? oi : mi;
+    }
+    if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
+    if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish the raw candidate in slot r
+      Cand w = io.c[bl];
+      w.dist = bk;
+      write_raw_slot(es.con[r], w, C, bl < 2 ? 0 : bl - 1);
+#pragma unroll
+      for (int i = 0; i < 4; i++) if (i == bl) cdist[i] = kInf;
+    }
+    if (mk < 0.f) ncon = r + 1;
+  }
+  return ncon;
+}
+
+// Rare path, one leg-leg contact: with A the arrow matrix already factorised in io.H (M + diagonal rows + world-vs-leg
+// contact blocks) and J, D the <=4 active pyramid-edge rows of that contact, (A + J^T D J) x = g is solved as
+//   (D^-1 + J A^-1 J^T) y = J A^-1 g ,  x = A^-1 (g - J^T y).
+// The rows have no base columns (the base moves both legs alike) and 3 entries on each of the two legs, held by those
+// legs' lanes.  Quads without such a contact run along with zero rows (y = 0).  Called by the whole warp; kept OUT OF
+// LINE with a memory-backed argument block so that its ~800 instructions stay out of the substep loop's address range
+// (the loop is instruction-fetch bound: tools/line_hist.py).  On exit io.tb / io.tl hold x.
+struct WoodburyIO {
+  TreeMat H;
+  float gb[6], gl[3];
+  S6 cd[3];
+  float tb[6], tl[3];  // in: A^-1 g ; out: the corrected solution
+};
+__device__ __noinline__ void woodbury_direction(const EnvShared &es, WoodburyIO &io, int part_all, int css, bool one_ss, int qbase, float ja) {
+  const unsigned qm = 0xffffffffu;
+  TreeMat H = io.H;
+  float gb[6], gl[3], tl[3];
+  S6 cd[3];
+#pragma unroll
+  for (int d = 0; d < 6; d++) gb[d] = io.gb[d];
+#pragma unroll
+  for (int j = 0; j < 3; j++) { gl[j] = io.gl[j]; tl[j] = io.tl[j]; cd[j] = io.cd[j]; }
+  const ContactSlot &s = es.con[css];
+  const int pc = (part_all >> (4 * css)) & 15;
+  const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
+  const float sg = one_ss ? ((d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f)) : 0.f;
+  const V3 r = V3{s.r[0], s.r[1], s.r[2]};
+  float cn[3], ct1[3], ct2[3];  // contact-frame components of this leg's columns
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    const V3 col = cd[j].l + cross(cd[j].a, r);
+    const float w = (dep != 0 && j <= dep) ? sg : 0.f;
+    cn[j] = w * (s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z);
+    ct1[j] = w * (s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z);
+    ct2[j] = w * (s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z);
+  }
+  const float de = (one_ss && ja < 0.f) ? s.D : 0.f;  // weight of this lane's edge (0: inactive)
+  float je[4][3], S[4][4], t[4], dinv[4];
+  const float zb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float dd = __shfl_sync(qm, de, qbase + e);
+    const float on = dd > 0.f ? 1.f : 0.f;
+    dinv[e] = dd > 0.f ? 1.f / dd : 1.f;
+    const float em = ((e & 1) ? -s.mu : s.mu) * on;
+#pragma unroll
+    for (int j = 0; j < 3; j++) je[e][j] = fmaf(em, (e >> 1) ? ct2[j] : ct1[j], on * cn[j]);
+    t[e] = qsum(je[e][0] * tl[0] + je[e][1] * tl[1] + je[e][2] * tl[2], qm);
+  }
+#pragma unroll 1
+  for (int e = 0; e < 4; e++) {
+    float ub[6], ul[3];
+    float jr[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; q++) if (q == e) { jr[0] = je[q][0]; jr[1] = je[q][1]; jr[2] = je[q][2]; }
+    tree_solve(H, zb, jr, ub, ul, qm);  // column e of A^-1 J^T
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float v = qsum(je[i][0] * ul[0] + je[i][1] * ul[1] + je[i][2] * ul[2], qm);
+      if (i <= e) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (q == e) S[q][i] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; e++) S[e][e] += dinv[e];
+  // 4x4 Cholesky of S (SPD: D^-1 > 0 on the diagonal, J A^-1 J^T >= 0) and the two triangular solves
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) {
+      float v = S[i][j];
+#pragma unroll
+      for (int q = 0; q < j; q++) v = fmaf(-S[i][q], S[j][q], v);
+      S[i][j] = (i == j) ? sqrtf(v) : v / S[j][j];
+    }
+  float y[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    float v = t[i];
+#pragma unroll
+    for (int q = 0; q < i; q++) v = fmaf(-S[i][q], y[q], v);
+    y[i] = v / S[i][i];
+  }
+#pragma unroll
+  for (int i = 3; i >= 0; i--) {
+    float v = y[i];
+#pragma unroll
+    for (int q = i + 1; q < 4; q++) v = fmaf(-S[q][i], y[q], v);
+    y[i] = v / S[i][i];
+  }
+  float g2[3];
+#pragma unroll
+  for (int j = 0; j < 3; j++) g2[j] = gl[j] - (y[0] * je[0][j] + y[1] * je[1][j] + y[2] * je[2][j] + y[3] * je[3][j]);
+  float xb2[6], xl2[3];
+  tree_solve(H, gb, g2, xb2, xl2, qm);
+#pragma unroll
+  for (int d = 0; d < 6; d++) io.tb[d] = xb2[d];
+#pragma unroll
+  for (int j = 0; j < 3; j++) io.tl[j] = xl2[j];
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One mjx.forward for the env of this quad.  Outputs qacc (ab, al).
 // ---------------------------------------------------------------------------------------------------
@@ -985,124 +1332,50 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   int part_all = 0;                 // participation code of this lane in every contact (4 bits per contact)
   bool plane_only = false;          // warp-uniform: the lists above were filled by the collision fast path
   {
-    float cdist[4];
-    V3 cpos[4], cn[4];
-    int ccode1[4], ccode2[4], cs1[4], cs2[4], ctype[4];
-    int cbox = 0;
-    // plane-sphere: own two spheres against z = 0
+    // Four candidates per lane: its own two spheres against the plane z = 0, the sphere-box pair ranked k by the broad
+    // phase, the leg-leg sphere pair ranked k.  The last two are rare (no boxes on flat terrain, legs seldom touch) and
+    // live out of line (box_candidate / ss_candidate), as does the ranking cut used when an env has more penetrating
+    // candidates than contact slots (cut_candidates).
+    Cand cd_[4];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       float r = m.sphere_radius[2 * k + i];
       float d = sc[i].z - r;
-      cdist[i] = d < 0.f ? d : kInf;
-      cn[i] = V3{0.f, 0.f, 1.f};
-      cpos[i] = sc[i] - (r + 0.5f * d) * cn[i];
-      ccode1[i] = -1; ccode2[i] = k * 4 + 1 + i; cs1[i] = -1; cs2[i] = 2 * k + i; ctype[i] = 0;
+      cd_[i].dist = d < 0.f ? d : kInf;
+      cd_[i].n = V3{0.f, 0.f, 1.f};
+      cd_[i].pos = sc[i] - (r + 0.5f * d) * cd_[i].n;
+      cd_[i].code1 = -1; cd_[i].code2 = k * 4 + 1 + i; cd_[i].s1 = -1; cd_[i].s2 = 2 * k + i; cd_[i].box = 0;
     }
-    cdist[2] = kInf; cdist[3] = kInf;
-    ccode1[2] = ccode2[2] = cs1[2] = cs2[2] = -1; ctype[2] = 1; cpos[2] = cn[2] = V3{0.f, 0.f, 0.f};
-    ccode1[3] = ccode2[3] = cs1[3] = cs2[3] = -1; ctype[3] = 2; cpos[3] = cn[3] = V3{0.f, 0.f, 0.f};
-    const int maxp = m.max_geom_pairs;
-    // sphere-box: broad phase keeps the max_geom_pairs pairs with the smallest bounding-sphere distance over all
-    // 8*nbox pairs (pair index = sphere*nbox + box, ties to the lower index); the pair of rank i gets narrow phase on
-    // lane i.  One pass per lane keeps its own 4 best pairs sorted, a 4-round merge over the quad ranks them, and the
-    // 4 narrow phases then run side by side.
-    if (m.nbox > 0) {
-      const int nbox = m.nbox;
-      float k0 = kInf, k1 = kInf, k2 = kInf, k3 = kInf;
-      int i0 = 0x7fffffff, i1 = 0x7fffffff, i2 = 0x7fffffff, i3 = 0x7fffffff;
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        const float rs = m.sphere_radius[2 * k + i];
-#pragma unroll 1
-        for (int bx = 0; bx < nbox; bx++) {
-          V3 d = V3{m.box_pos[bx][0], m.box_pos[bx][1], m.box_pos[bx][2]} - sc[i];
-          const float key = sqrtf(dot(d, d)) - (rs + sh.d.box_rbound[bx]);
-          const int id = (2 * k + i) * nbox + bx;  // ids grow along the pass, so strict '<' keeps ties in index order
-          const bool c0 = key < k0, c1 = key < k1, c2 = key < k2, c3 = key < k3;
-          k3 = c2 ? k2 : (c3 ? key : k3); i3 = c2 ? i2 : (c3 ? id : i3);
-          k2 = c1 ? k1 : (c2 ? key : k2); i2 = c1 ? i1 : (c2 ? id : i2);
-          k1 = c0 ? k0 : (c1 ? key : k1); i1 = c0 ? i0 : (c1 ? id : i1);
-          k0 = c0 ? key : k0; i0 = c0 ? id : i0;
-        }
-      }
-      const int nr = min(min(maxp, 4), 8 * nbox);
-      int mine = -1;
-#pragma unroll 1
-      for (int r = 0; r < nr; r++) {
-        float bk = k0;
-        int bi = i0;
-#pragma unroll
-        for (int s = 1; s <= 2; s <<= 1) {
-          float ok = __shfl_xor_sync(qm, bk, s);
-          int oi = __shfl_xor_sync(qm, bi, s);
-          if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-        }
-        if (bi == i0) { k0 = k1; i0 = i1; k1 = k2; i1 = i2; k2 = k3; i2 = i3; k3 = kInf; i3 = 0x7fffffff; }  // this lane's head won: pop it
-        if (r == k) mine = bi;
-      }
-      if (mine >= 0) {  // narrow phase of the pair ranked k
-        const int sph = mine / nbox, bx = mine - sph * nbox;
-        V3 c = V3{es.sph[sph][0], es.sph[sph][1], es.sph[sph][2]};
-        V3 pp, nn;
-        float d = sphere_box(c, m.sphere_radius[sph], m.box_pos[bx], m.box_mat[bx], m.box_size[bx], pp, nn);
-        cdist[2] = d < 0.f ? d : kInf;
-        cpos[2] = pp; cn[2] = nn;
-        ccode1[2] = (sph >> 1) * 4 + 1 + (sph & 1); ccode2[2] = -1; cs1[2] = sph; cs2[2] = -1; cbox = bx;
-      }
+    for (int i = 2; i < 4; i++) {
+      cd_[i].dist = kInf; cd_[i].pos = cd_[i].n = V3{0.f, 0.f, 0.f};
+      cd_[i].code1 = cd_[i].code2 = cd_[i].s1 = cd_[i].s2 = -1; cd_[i].box = 0;
+    }
+    if (m.nbox > 0) {  // warp-uniform (a model property)
+      Cand io;
+      box_candidate(sh, es, k, qbase, sc[0], sc[1], io);
+      cd_[2] = io;
     }
     // sphere-sphere: 24 leg-leg pairs, 6 per lane in MJX pair order; nothing to do unless one penetrates
     {
-      float pd[6];
-      int pa[6], pb[6];
       bool any_neg = false;
 #pragma unroll
       for (int i = 0; i < 6; i++) {
         const int ab = sh.d.ss_pair[6 * k + i];  // pair 6k+i of the MJX pair list
         const int a = ab & 255, b = ab >> 8;
         V3 d = V3{es.sph[b][0] - es.sph[a][0], es.sph[b][1] - es.sph[a][1], es.sph[b][2] - es.sph[a][2]};
-        pd[i] = sqrtf(dot(d, d)) - (m.sphere_radius[a] + m.sphere_radius[b]);
-        pa[i] = a; pb[i] = b;
-        any_neg |= pd[i] < 0.f;
+        const float rr = m.sphere_radius[a] + m.sphere_radius[b];
+        any_neg |= dot(d, d) < rr * rr;  // |d| - rr < 0 (rr > 0); the out-of-line path recomputes the distances exactly
       }
       if (__any_sync(qm, any_neg)) {  // warp-uniform
-        uint32_t taken = 0u;
-        for (int r = 0; r < maxp && r < 24; r++) {
-          float bk = kInf;
-          int bi = 0x7fffffff;
-#pragma unroll
-          for (int i = 0; i < 6; i++)
-            if (!((taken >> i) & 1u) && (pd[i] < bk || (pd[i] == bk && 6 * k + i < bi))) { bk = pd[i]; bi = 6 * k + i; }
-#pragma unroll
-          for (int s = 1; s <= 2; s <<= 1) {
-            float ok = __shfl_xor_sync(qm, bk, s);
-            int oi = __shfl_xor_sync(qm, bi, s);
-            if (ok < bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-          }
-          int owner = min(bi / 6, 3), li = bi - owner * 6;
-          int a = 0, b = 0;
-#pragma unroll
-          for (int i = 0; i < 6; i++) if (i == li) { a = pa[i]; b = pb[i]; }
-          a = __shfl_sync(qm, a, qbase + owner);
-          b = __shfl_sync(qm, b, qbase + owner);
-          if (owner == k) taken |= 1u << li;
-          if ((r & 3) == k && r < 4 && bk < 0.f) {
-            V3 ca_ = V3{es.sph[a][0], es.sph[a][1], es.sph[a][2]}, cb_ = V3{es.sph[b][0], es.sph[b][1], es.sph[b][2]};
-            V3 n = cb_ - ca_;
-            float dn = normalize3(n);
-            if (dn == 0.f) n = V3{1.f, 0.f, 0.f};
-            float d = dn - (m.sphere_radius[a] + m.sphere_radius[b]);
-            cdist[3] = d < 0.f ? d : kInf;
-            cn[3] = n;
-            cpos[3] = ca_ + (m.sphere_radius[a] + d * 0.5f) * n;
-            ccode1[3] = (a >> 1) * 4 + 1 + (a & 1); ccode2[3] = (b >> 1) * 4 + 1 + (b & 1); cs1[3] = a; cs2[3] = b;
-          }
-        }
+        Cand io;
+        ss_candidate(sh, es, k, qbase, io);
+        cd_[3] = io;
       }
     }
     // final cut: the max_contact_points smallest dist over [plane 0..7, box 8..11, sphere-sphere 12..15]
     const int maxc = m.max_contact_points;
-    const bool a0 = cdist[0] < kInf, a1 = cdist[1] < kInf, a2 = cdist[2] < kInf, a3 = cdist[3] < kInf;
+    const bool a0 = cd_[0].dist < kInf, a1 = cd_[1].dist < kInf, a2 = cd_[2].dist < kInf, a3 = cd_[3].dist < kInf;
     const unsigned q0 = (__ballot_sync(qm, a0) >> qbase) & 15u, q1b = (__ballot_sync(qm, a1) >> qbase) & 15u;
     const unsigned q2 = (__ballot_sync(qm, a2) >> qbase) & 15u, q3 = (__ballot_sync(qm, a3) >> qbase) & 15u;
     const int nplane = __popc(q0) + __popc(q1b), total = nplane + __popc(q2) + __popc(q3);
@@ -1114,19 +1387,15 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       const int s0 = __popc(q0 & below) + __popc(q1b & below), s1 = s0 + (a0 ? 1 : 0);
       const int s2 = nplane + __popc(q2 & below), s3 = nplane + __popc(q2) + __popc(q3 & below);
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const bool on = i == 0 ? a0 : (i == 1 ? a1 : (i == 2 ? a2 : a3));
-        const int slot = i == 0 ? s0 : (i == 1 ? s1 : (i == 2 ? s2 : s3));
-        if (on) {
-          ContactSlot &s = es.con[slot];
-          s.r[0] = cpos[i].x - C.x; s.r[1] = cpos[i].y - C.y; s.r[2] = cpos[i].z - C.z;
-          s.frame[0] = cn[i].x; s.frame[1] = cn[i].y; s.frame[2] = cn[i].z;
-          s.dist = cdist[i];
-          s.code1 = ccode1[i]; s.code2 = ccode2[i]; s.s1 = cs1[i]; s.s2 = cs2[i]; s.ty = ctype[i]; s.box = cbox;
-        }
+      for (int i = 0; i < 2; i++) {
+        const bool on = i == 0 ? a0 : a1;
+        const int slot = i == 0 ? s0 : s1;
+        if (on) write_raw_slot(es.con[slot], cd_[i], C, 0);
       }
-      ncon = total;
-      if (!__any_sync(qm, a2 | a3)) {  // plane contacts only: each lane knows its own contacts without looking at the slots
+      if (__any_sync(qm, a2 | a3)) {  // rare: box or leg-leg candidates
+        if (a2) write_raw_slot(es.con[s2], cd_[2], C, 1);
+        if (a3) write_raw_slot(es.con[s3], cd_[3], C, 2);
+      } else {  // plane contacts only: each lane knows its own contacts without looking at the slots
         plane_only = true;
         own_count = (a0 ? 1 : 0) + (a1 ? 1 : 0);
         own_list = a0 ? (s0 | (a1 ? s1 << 3 : 0)) : (a1 ? s1 : 0);
@@ -1135,35 +1404,12 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         const float th = (a0 ? (float)((sh.c.torso_sphere_mask >> (2 * k)) & 1u) : 0.f) + (a1 ? (float)((sh.c.torso_sphere_mask >> (2 * k + 1)) & 1u) : 0.f);
         knee_hits = qsum(kh, qm); torso_hits = qsum(th, qm);
       }
+      ncon = total;
     } else {
-      for (int r = 0; r < maxc; r++) {
-        // local best of this lane's 4 candidates (ids grow with i, so the first minimum is also the lowest id)
-        const float bk = fminf(fminf(cdist[0], cdist[1]), fminf(cdist[2], cdist[3]));
-        const int bl = cdist[0] == bk ? 0 : (cdist[1] == bk ? 1 : (cdist[2] == bk ? 2 : 3));
-        const int bi = bk < kInf ? (bl < 2 ? 2 * k + bl : (bl == 2 ? 8 + k : 12 + k)) : 0x7fffffff;
-        float mk = bk;
-        int mi = bi;
+      CutIO io;
 #pragma unroll
-        for (int s = 1; s <= 2; s <<= 1) {
-          float ok = __shfl_xor_sync(qm, mk, s);
-          int oi = __shfl_xor_sync(qm, mi, s);
-          const bool take = (ok < mk) | ((ok == mk) & (oi < mi));
-          mk = take ? ok : mk; mi = take ? oi : mi;
-        }
-        if (!__any_sync(qm, mk < 0.f)) break;  // warp-uniform exit
-        if (mk < 0.f && mi == bi && bk < 0.f) {  // this lane owns the winner: publish the raw candidate in slot r
-          ContactSlot &s = es.con[r];
-          V3 pp = V3{0.f, 0.f, 0.f}, nn = V3{0.f, 0.f, 1.f};
-          int c1 = -1, c2 = -1, s1 = -1, s2 = -1, ty = 0;
-#pragma unroll
-          for (int i = 0; i < 4; i++) if (i == bl) { pp = cpos[i]; nn = cn[i]; c1 = ccode1[i]; c2 = ccode2[i]; s1 = cs1[i]; s2 = cs2[i]; ty = ctype[i]; cdist[i] = kInf; }
-          s.r[0] = pp.x - C.x; s.r[1] = pp.y - C.y; s.r[2] = pp.z - C.z;
-          s.frame[0] = nn.x; s.frame[1] = nn.y; s.frame[2] = nn.z;
-          s.dist = bk;
-          s.code1 = c1; s.code2 = c2; s.s1 = s1; s.s2 = s2; s.ty = ty; s.box = cbox;
-        }
-        if (mk < 0.f) ncon = r + 1;
-      }
+      for (int i = 0; i < 4; i++) io.c[i] = cd_[i];
+      ncon = cut_candidates(es, k, qbase, maxc, C, io);
     }
   }
   __syncwarp(qm);  // raw contact slots visible to the quad
@@ -1198,20 +1444,11 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     }
   }
   __syncwarp(qm);  // completed contact slots visible to the quad
-  if (!plane_only) {
-#pragma unroll 1
-    for (int c = 0; c < ncon; c++) {
-      const ContactSlot &s = es.con[c];
-      const bool is_ss = (s.code1 >= 0 && s.code2 >= 0);
-      if (is_ss) { n_ss++; css = c; ss_mask |= 1 << c; }
-      {
-        const int pc = participation(s, k);
-        part_all |= pc << (4 * c);
-        if (pc && !is_ss) { own_list |= c << (3 * own_count); own_count++; }
-      }
-      if (s.s1 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s1) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s1) & 1u); }
-      if (s.s2 >= 0) { knee_hits += (float)((sh.c.knee_sphere_mask >> s.s2) & 1u); torso_hits += (float)((sh.c.torso_sphere_mask >> s.s2) & 1u); }
-    }
+  if (!plane_only) {  // rare (boxes, leg-leg contacts, ranking cut): derive this lane's lists from the slots, out of line
+    SlotScan sc_;
+    scan_slots(sh.c.knee_sphere_mask, sh.c.torso_sphere_mask, es, ncon, k, sc_);
+    n_ss = sc_.n_ss; css = sc_.css; ss_mask = sc_.ss_mask; part_all = sc_.part_all; own_list = sc_.own_list; own_count = sc_.own_count;
+    knee_hits = sc_.knee_hits; torso_hits = sc_.torso_hits;
   }
 
   // A leg-leg contact couples two legs, so its rows do not fit the arrow structure.  One such contact (the common
@@ -1239,12 +1476,10 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     float dlo = L.ql[j] - m.jnt_range[3 * k + j][0], dhi = m.jnt_range[3 * k + j][1] - L.ql[j];
     float p = fminf(dlo, dhi);
     lsign[j] = 0.f; lD[j] = 0.f; lA[j] = 0.f;
-    if (p < 0.f) {
-      float kk, bb, imp;
+    if (p < 0.f) {  // joint past a limit (rare): efc_D and aref of its row, out of line
       lsign[j] = dlo < dhi ? 1.f : -1.f;
-      kbi(m.jnt_solref, m.jnt_solimp, dt, p, kk, bb, imp);
-      lD[j] = 1.f / fmaxf(m.dof_invweight0[d] * (1.f - imp) / imp, kMinVal);
-      lA[j] = -bb * (lsign[j] * L.vl[j]) - kk * imp * p;
+      const float2 r = limit_row(m.jnt_solref, m.jnt_solimp, dt, p, lsign[j] * L.vl[j], m.dof_invweight0[d]);
+      lD[j] = r.x; lA[j] = r.y;
     }
   }
 
@@ -1271,7 +1506,19 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     // contact rows at qvel / warm start / qacc_smooth, their reference accelerations and both start costs: world-vs-leg
     // contacts by the touching leg's lane (all four edges), leg-leg contacts edge by edge with a sum over the quad
     contact_rows_own<3, true>(es, cd, ba, bo, v3b, v3l, own_list, own_count, nown_w, part_all, rowQ, cw_con, cs_con);
-    if (ss_mask_w) contact_rows_legleg<3>(es, cd, ba, bo, v3b, v3l, esgn, et2, qm, part_all, ss_mask, ss_mask_w, rowA);
+    if (ss_mask_w) {  // leg-leg contact somewhere in the warp (rare): out of line, arguments through memory
+      LegLegIO<3> io;
+#pragma unroll
+      for (int j = 0; j < 3; j++) { io.cd[j] = cd[j]; io.ba[j] = ba[j]; io.bo[j] = bo[j]; }
+#pragma unroll
+      for (int n = 0; n < 3; n++) {
+#pragma unroll
+        for (int d = 0; d < 6; d++) io.vb[n][d] = v3b[n][d];
+#pragma unroll
+        for (int j = 0; j < 3; j++) io.vl[n][j] = v3l[n][j];
+      }
+      legleg_rows3(es, io, esgn, et2, part_all, ss_mask, ss_mask_w, rowA);
+    }
   }
   float cost_w, cost_s, gauss_w;
   float jaw_f[3], jaw_l[3], jas_f[3], jas_l[3];
@@ -1296,18 +1543,9 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
         cs = fmaf(0.5f * lD[j] * ms, ms, cs);
       }
     }
-    if (ss_mask_w) {  // leg-leg slots hold raw rows: turn this lane's edge into Jaref and add its cost
-#pragma unroll 1
-      for (int rem = ss_mask; rem; rem &= rem - 1) {
-        const int c = __ffs(rem) - 1;
-        const ContactSlot &s = es.con[c];
-        float aref = -s.b * rowA[c * kBlock] - s.kimp;
-        float xw = rowB[c * kBlock] - aref, xs = rowC[c * kBlock] - aref;
-        rowB[c * kBlock] = xw; rowC[c * kBlock] = xs;
-        const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
-        cw = fmaf(0.5f * s.D * mw, mw, cw);
-        cs = fmaf(0.5f * s.D * ms, ms, cs);
-      }
+    if (ss_mask_w) {  // leg-leg slots hold raw rows: turn this lane's edge into Jaref and add its cost (rare, out of line)
+      const float2 dc = legleg_start_cost(es, ss_mask, rowA);
+      cw += dc.x; cs += dc.y;
     }
     __syncwarp(qm);  // Jaref rows written by the owning lanes are visible to every edge's lane
     float gw = 0.f;
@@ -1472,25 +1710,10 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     Sb = qsum6(Sb, qm);  // the base carries every world-vs-leg contact
     if (ss_mask_w) {
       // Leg-leg contacts: equal and opposite wrenches on the two legs' chains, nothing on the base (its columns cancel).
-      // Their Hessian rows couple two legs: Woodbury / dense paths below.
-#pragma unroll 1
-      for (int rem = ss_mask; rem; rem &= rem - 1) {
-        const int c = __ffs(rem) - 1;
-        const ContactSlot &s = es.con[c];
-        const float *ja = rowJ - k + c * kBlock;
-        const float D = s.D, mu = s.mu;
-        const float f0 = -D * fminf(ja[0], 0.f), f1 = -D * fminf(ja[1], 0.f), f2 = -D * fminf(ja[2], 0.f), f3 = -D * fminf(ja[3], 0.f);
-        const float Fn = (f0 + f1) + (f2 + f3), Ft1 = mu * (f0 - f1), Ft2 = mu * (f2 - f3);
-        const V3 g = V3{s.frame[0] * Fn + s.frame[3] * Ft1 + s.frame[6] * Ft2, s.frame[1] * Fn + s.frame[4] * Ft1 + s.frame[7] * Ft2,
-                        s.frame[2] * Fn + s.frame[5] * Ft1 + s.frame[8] * Ft2};
-        const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-        const S6 w = S6{cross(r, g), g};
-        const int pc = (part_all >> (4 * c)) & 15;
-        const int dd1 = pc & 3, dd2 = (pc >> 2) & 3;
-        const float s1w = (dd2 == 1 ? 1.f : 0.f) - (dd1 == 1 ? 1.f : 0.f), s2w = (dd2 == 2 ? 1.f : 0.f) - (dd1 == 2 ? 1.f : 0.f);
-        S1 = fma6(s1w, w, S1);
-        S2 = fma6(s2w, w, S2);
-      }
+      // Their Hessian rows couple two legs: Woodbury / dense paths below.  Rare, out of line.
+      S6 io[2] = {S1, S2};
+      legleg_wrench(es, ss_mask, rowJ - k, part_all, io);
+      S1 = io[0]; S2 = io[1];
     }
     // qfrc_constraint and gradient
     gl[0] = Mal[0] - fs_l[0] - (qc_l[0] + dot6(cd[0], S1 + S2));
@@ -1521,83 +1744,19 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   {
     float tb[6], tl[3];
     tree_solve(H, gb, gl, tb, tl, qm);
-    if (__any_sync(qm, one_ss)) {
-      // Rare: one leg-leg contact.  With A the arrow matrix just factorised (M + diagonal rows + world-vs-leg contact
-      // blocks) and J, D the <=4 active pyramid-edge rows of that contact, (A + J^T D J) x = g is solved as
-      //   (D^-1 + J A^-1 J^T) y = J A^-1 g ,  x = A^-1 (g - J^T y).
-      // The rows have no base columns (the base moves both legs alike) and 3 entries on each of the two legs, held by
-      // those legs' lanes.  Quads without such a contact run along with zero rows (y = 0).
-      const ContactSlot &s = es.con[css];
-      const int pc = (part_all >> (4 * css)) & 15;
-      const int d1 = pc & 3, d2 = (pc >> 2) & 3, dep = d1 | d2;
-      const float sg = one_ss ? ((d2 ? 1.f : 0.f) - (d1 ? 1.f : 0.f)) : 0.f;
-      const V3 r = V3{s.r[0], s.r[1], s.r[2]};
-      float cn[3], ct1[3], ct2[3];  // contact-frame components of this leg's columns
+    if (__any_sync(qm, one_ss)) {  // rare: one leg-leg contact in some env of the warp -> rank-<=4 Woodbury correction, out of line
+      WoodburyIO io;
+      io.H = H;
 #pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const V3 col = cd[j].l + cross(cd[j].a, r);
-        const float w = (dep != 0 && j <= dep) ? sg : 0.f;
-        cn[j] = w * (s.frame[0] * col.x + s.frame[1] * col.y + s.frame[2] * col.z);
-        ct1[j] = w * (s.frame[3] * col.x + s.frame[4] * col.y + s.frame[5] * col.z);
-        ct2[j] = w * (s.frame[6] * col.x + s.frame[7] * col.y + s.frame[8] * col.z);
-      }
-      const float ja = rowJ[css * kBlock];
-      const float de = (one_ss && ja < 0.f) ? s.D : 0.f;  // weight of this lane's edge (0: inactive)
-      float je[4][3], S[4][4], t[4], dinv[4];
-      const float zb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int d = 0; d < 6; d++) { io.gb[d] = gb[d]; io.tb[d] = tb[d]; }
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const float dd = __shfl_sync(qm, de, qbase + e);
-        const float on = dd > 0.f ? 1.f : 0.f;
-        dinv[e] = dd > 0.f ? 1.f / dd : 1.f;
-        const float em = ((e & 1) ? -s.mu : s.mu) * on;
-#pragma unroll
-        for (int j = 0; j < 3; j++) je[e][j] = fmaf(em, (e >> 1) ? ct2[j] : ct1[j], on * cn[j]);
-        t[e] = qsum(je[e][0] * tl[0] + je[e][1] * tl[1] + je[e][2] * tl[2], qm);
-      }
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        float ub[6], ul[3];
-        tree_solve(H, zb, je[e], ub, ul, qm);  // column e of A^-1 J^T
-#pragma unroll
-        for (int i = 0; i <= e; i++) S[e][i] = qsum(je[i][0] * ul[0] + je[i][1] * ul[1] + je[i][2] * ul[2], qm);
-        S[e][e] += dinv[e];
-      }
-      // 4x4 Cholesky of S (SPD: D^-1 > 0 on the diagonal, J A^-1 J^T >= 0) and the two triangular solves
-#pragma unroll
-      for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) {
-          float v = S[i][j];
-#pragma unroll
-          for (int q = 0; q < j; q++) v = fmaf(-S[i][q], S[j][q], v);
-          S[i][j] = (i == j) ? sqrtf(v) : v / S[j][j];
-        }
-      float y[4];
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        float v = t[i];
-#pragma unroll
-        for (int q = 0; q < i; q++) v = fmaf(-S[i][q], y[q], v);
-        y[i] = v / S[i][i];
-      }
-#pragma unroll
-      for (int i = 3; i >= 0; i--) {
-        float v = y[i];
-#pragma unroll
-        for (int q = i + 1; q < 4; q++) v = fmaf(-S[q][i], y[q], v);
-        y[i] = v / S[i][i];
-      }
-      float g2[3];
-#pragma unroll
-      for (int j = 0; j < 3; j++) g2[j] = gl[j] - (y[0] * je[0][j] + y[1] * je[1][j] + y[2] * je[2][j] + y[3] * je[3][j]);
-      float xb2[6], xl2[3];
-      tree_solve(H, gb, g2, xb2, xl2, qm);
+      for (int j = 0; j < 3; j++) { io.gl[j] = gl[j]; io.tl[j] = tl[j]; io.cd[j] = cd[j]; }
+      woodbury_direction(es, io, part_all, css, one_ss, qbase, rowJ[css * kBlock]);
       if (one_ss) {
 #pragma unroll
-        for (int d = 0; d < 6; d++) tb[d] = xb2[d];
+        for (int d = 0; d < 6; d++) tb[d] = io.tb[d];
 #pragma unroll
-        for (int j = 0; j < 3; j++) tl[j] = xl2[j];
+        for (int j = 0; j < 3; j++) tl[j] = io.tl[j];
       }
     }
     if (!dense_env) {
@@ -1626,7 +1785,14 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       for (int j = 0; j < 3; j++) v1l[0][j] = hl[j];
       float unused0 = 0.f, unused1 = 0.f;
       contact_rows_own<1, false>(es, cd, ba, bo, v1b, v1l, own_list, own_count, nown_w, part_all, rowQ, unused0, unused1);  // jv of the contact-edge rows
-      if (ss_mask_w) contact_rows_legleg<1>(es, cd, ba, bo, v1b, v1l, esgn, et2, qm, part_all, ss_mask, ss_mask_w, rowA);
+      if (ss_mask_w) {
+        LegLegIO<1> io;
+#pragma unroll
+        for (int j = 0; j < 3; j++) { io.cd[j] = cd[j]; io.ba[j] = ba[j]; io.bo[j] = bo[j]; io.vl[0][j] = hl[j]; }
+#pragma unroll
+        for (int d = 0; d < 6; d++) io.vb[0][d] = hb[d];
+        legleg_rows1(es, io, esgn, et2, part_all, ss_mask, ss_mask_w, rowA);
+      }
       __syncwarp(qm);
     }
     float sn = hl[0] * hl[0] + hl[1] * hl[1] + hl[2] * hl[2];

@@ -21,7 +21,7 @@ assert len(locs) == len(data), (len(locs), len(data))
 # phase boundaries from the source markers
 ksrc = open(os.path.join(os.path.dirname(lib), "csrc", "pupper_kernel.cuh")).read().splitlines()
 marks = [(i + 1, l.strip()[8:60]) for i, l in enumerate(ksrc) if l.startswith("  // ---- ")]
-fstart = next(i + 1 for i, l in enumerate(ksrc) if "void forward(" in l)
+fstart = next(i + 1 for i, l in enumerate(ksrc) if " forward(const BlockShared" in l)
 def phase_of(f, l, prev):
     if f == "pupper_env.cu": return "env-level (pupper_env.cu)"
     if f == "pupper_kernel.cuh":
