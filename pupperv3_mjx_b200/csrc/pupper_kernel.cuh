@@ -1356,17 +1356,23 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       box_candidate(sh, es, k, qbase, sc[0], sc[1], io);
       cd_[2] = io;
     }
-    // sphere-sphere: 24 leg-leg pairs, 6 per lane in MJX pair order; nothing to do unless one penetrates
+    // sphere-sphere: 24 leg-leg pairs; nothing to do unless one penetrates.  For that test the pairs are dealt to the lanes
+    // by symmetry (own spheres against both spheres of the next leg, and half of the four pairs with the opposite leg), the
+    // other legs' centres come by shuffle; the out-of-line path then ranks the pairs in MJX order.
     {
-      bool any_neg = false;
-#pragma unroll
-      for (int i = 0; i < 6; i++) {
-        const int ab = sh.d.ss_pair[6 * k + i];  // pair 6k+i of the MJX pair list
-        const int a = ab & 255, b = ab >> 8;
-        V3 d = V3{es.sph[b][0] - es.sph[a][0], es.sph[b][1] - es.sph[a][1], es.sph[b][2] - es.sph[a][2]};
-        const float rr = m.sphere_radius[a] + m.sphere_radius[b];
-        any_neg |= dot(d, d) < rr * rr;  // |d| - rr < 0 (rr > 0); the out-of-line path recomputes the distances exactly
-      }
+      const int n1 = qbase | ((k + 1) & 3), n2 = qbase | ((k + 2) & 3);
+      const float rK = m.sphere_radius[2 * k], rF = m.sphere_radius[2 * k + 1];
+      const V3 aK = V3{__shfl_sync(qm, sc[0].x, n1), __shfl_sync(qm, sc[0].y, n1), __shfl_sync(qm, sc[0].z, n1)};
+      const V3 aF = V3{__shfl_sync(qm, sc[1].x, n1), __shfl_sync(qm, sc[1].y, n1), __shfl_sync(qm, sc[1].z, n1)};
+      const V3 oK = V3{__shfl_sync(qm, sc[0].x, n2), __shfl_sync(qm, sc[0].y, n2), __shfl_sync(qm, sc[0].z, n2)};
+      const V3 oF = V3{__shfl_sync(qm, sc[1].x, n2), __shfl_sync(qm, sc[1].y, n2), __shfl_sync(qm, sc[1].z, n2)};
+      const float raK = __shfl_sync(qm, rK, n1), raF = __shfl_sync(qm, rF, n1), roK = __shfl_sync(qm, rK, n2), roF = __shfl_sync(qm, rF, n2);
+      auto pen = [](V3 p, V3 q, float rr) { const V3 d = p - q; return dot(d, d) < rr * rr; };  // |d| - rr < 0 (rr > 0)
+      bool any_neg = pen(sc[0], aK, rK + raK) | pen(sc[0], aF, rK + raF) | pen(sc[1], aK, rF + raK) | pen(sc[1], aF, rF + raF);
+      // opposite leg: lanes 0,1 test (own knee, its knee) (own knee, its foot); lanes 2,3 (own knee, its foot) (own foot, its foot)
+      const bool lowk = k < 2;
+      any_neg |= pen(sc[0], lowk ? oK : oF, rK + (lowk ? roK : roF));
+      any_neg |= pen(lowk ? sc[0] : sc[1], oF, (lowk ? rK : rF) + roF);
       if (__any_sync(qm, any_neg)) {  // warp-uniform
         Cand io;
         ss_candidate(sh, es, k, qbase, io);

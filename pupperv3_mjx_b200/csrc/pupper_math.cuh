@@ -187,7 +187,9 @@ __device__ __forceinline__ void sincos_small(float x, float *sn, float *cs) {
 }
 
 // ---- jax 0.5.0 threefry2x32 (partitionable derivation), SURVEY.md A.11 ------------------------------
-__device__ __forceinline__ uint2 threefry2x32(uint2 key, uint32_t c0, uint32_t c1) {
+// Out of line on purpose: the env-level code calls it ~15 times per step, and inlined copies (~75 instructions each) only add
+// code for the instruction caches to stream (the step is instruction-fetch bound).
+__device__ __noinline__ uint2 threefry2x32(uint2 key, uint32_t c0, uint32_t c1) {
   const uint32_t ks0 = key.x, ks1 = key.y, ks2 = key.x ^ key.y ^ 0x1BD11BDAu;
   uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
 #define TF_R(r) x0 += x1; x1 = __funnelshift_l(x1, x1, r); x1 ^= x0;
