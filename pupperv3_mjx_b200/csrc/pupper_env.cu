@@ -181,17 +181,14 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
   {
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(p.model);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.m);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < (int)(sizeof(PupperModelDesc) / 4); i += kBlock) dst[i] = __ldg(src + i);
-    src = reinterpret_cast<const uint32_t *>(p.cfg);
-    dst = reinterpret_cast<uint32_t *>(&sh.c);
-#pragma unroll 2
-    for (int i = threadIdx.x; i < (int)(sizeof(PupperEnvCfg) / 4); i += kBlock) dst[i] = __ldg(src + i);
-    src = reinterpret_cast<const uint32_t *>(p.derived);
-    dst = reinterpret_cast<uint32_t *>(&sh.d);
-    for (int i = threadIdx.x; i < (int)(sizeof(DerivedConsts) / 4); i += kBlock) dst[i] = __ldg(src + i);
+    const uint4 *src = reinterpret_cast<const uint4 *>(p.consts);
+    uint4 *dst = reinterpret_cast<uint4 *>(static_cast<ConstBlock *>(&sh));
+    constexpr int n16 = (int)(sizeof(ConstBlock) / 16);
+#pragma unroll
+    for (int i0 = 0; i0 < n16; i0 += kBlock) {
+      const int i = i0 + threadIdx.x;
+      if (i < n16) dst[i] = __ldg(src + i);
+    }
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, k = threadIdx.x & 3;
@@ -211,30 +208,27 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   const int ext_s = (DBG && p.has_rand) ? p.rand.stride : 0;
 
   // ---- stage the per-env DR leaves (or the nominal values) in shared memory --------------------------
-  // (two phases so the up-to-15 global loads of a lane are all in flight before the first is consumed)
+  // Rolled loops on purpose (code size); the per-env leaves travel global -> shared as 4-byte async copies, so the
+  // up-to-15 loads of a lane are all in flight at once without passing through registers.
   {
     float *ef = reinterpret_cast<float *>(&es);  // mass[13] inertia[39] ipos[3] friction kp kd are contiguous
-    float v[15];
-#pragma unroll
-    for (int t = 0; t < 15; t++) {
-      const int i = k + 4 * t;
-      v[t] = 0.f;
-      if (i < 58) {
-        if (p.has_dr) {
-          const int ds = p.dr.stride;
-          const float *src = i < 13 ? p.dr.body_mass + (size_t)i * ds
-                           : i < 52 ? p.dr.body_inertia + (size_t)(i - 13) * ds
-                           : i < 55 ? p.dr.base_ipos + (size_t)(i - 52) * ds
-                           : i == 55 ? p.dr.friction : (i == 56 ? p.dr.kp : p.dr.kd);
-          v[t] = __ldg(src + e);
-        } else {
-          v[t] = i < 13 ? m.body_mass[1 + i] : i < 52 ? m.body_inertia[1 + (i - 13) / 3][(i - 13) % 3]
-               : i < 55 ? m.body_ipos[1][i - 52] : i == 55 ? -1.f : (i == 56 ? m.act_gain[0] : -m.act_bias2[0]);
-        }
+    if (p.has_dr) {
+      const int ds = p.dr.stride;
+#pragma unroll 1
+      for (int i = k; i < 58; i += 4) {
+        const float *src = i < 13 ? p.dr.body_mass + (size_t)i * ds
+                         : i < 52 ? p.dr.body_inertia + (size_t)(i - 13) * ds
+                         : i < 55 ? p.dr.base_ipos + (size_t)(i - 52) * ds
+                         : i == 55 ? p.dr.friction : (i == 56 ? p.dr.kp : p.dr.kd);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(ef + i)), "l"(src + e) : "memory");
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+#pragma unroll 1
+      for (int i = k; i < 58; i += 4)
+        ef[i] = i < 13 ? m.body_mass[1 + i] : i < 52 ? m.body_inertia[1 + (i - 13) / 3][(i - 13) % 3]
+              : i < 55 ? m.body_ipos[1][i - 52] : i == 55 ? -1.f : (i == 56 ? m.act_gain[0] : -m.act_bias2[0]);
     }
-#pragma unroll
-    for (int t = 0; t < 15; t++) if (k + 4 * t < 58) ef[k + 4 * t] = v[t];
   }
   // Contact slots are read (and multiplied by zero weights) by quads that have fewer contacts than the warp
   // maximum, so they must never hold non-finite garbage: clear them once per launch.
@@ -243,6 +237,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     for (int i = k; i < (int)(sizeof(es.con) / 4); i += 4) cz[i] = 0.f;
     if (k == 0) es.ncon = 0;
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp(qm);
 
   LaneState L;
@@ -309,15 +304,20 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     {
       auto pf = [](const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); };
       const int Li = c.n_imu_latency;
-      for (int l = 0; l < Li; l++) { pf(p.st.imu_buffer + (size_t)(k * Li + l) * stride + e); if (k < 2) pf(p.st.imu_buffer + (size_t)((k + 4) * Li + l) * stride + e); }
+#pragma unroll 1
+      for (int r = k; r < 6; r += 4)
+#pragma unroll 1
+        for (int l = 0; l < Li; l++) pf(p.st.imu_buffer + (size_t)(r * Li + l) * stride + e);
+#pragma unroll 1
       for (int i = k * 32; i < H * PUPPER_OBS_DIM; i += 128) pf(p.st.obs + (size_t)e * H * PUPPER_OBS_DIM + i);
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < 3; j++) { pf(p.st.last_vel + (size_t)(3 * k + j) * stride + e); pf(p.st.last_act + (size_t)(3 * k + j) * stride + e); }
       if (k < 3) { pf(p.st.command + (size_t)k * stride + e); pf(p.st.desired_world_z + (size_t)k * stride + e); }
       pf(p.st.feet_air_time + (size_t)k * stride + e);
       if (k == 0) { pf(p.st.last_contact + e); pf(p.st.step + e); }
       if (p.has_ep) {
         const int es_ = p.ep.stride;
+#pragma unroll 1
         for (int i = k; i < PUPPER_NMETRIC; i += 4) pf(p.ep.sum_metrics + (size_t)i * es_ + e);
         if (k == 1) { pf(p.ep.episode_done + e); pf(p.ep.steps + e); }
         if (k == 2) { pf(p.ep.sum_reward + e); pf(p.ep.length + e); }
@@ -709,9 +709,7 @@ __global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float *sink)
 struct PupperModel {
   int smem_bytes;  // dynamic shared memory per CTA (sizeof(BlockShared) + optional PUPPER_EXTRA_SMEM padding, an occupancy experiment knob)
   int device;
-  PupperModelDesc *d_desc;
-  PupperEnvCfg *d_cfg;
-  pupper::DerivedConsts *d_derived;
+  pupper::ConstBlock *d_consts;  // model description + env configuration + derived constants, as the kernel stages them
   PupperModelDesc h_desc;
   PupperEnvCfg h_cfg;
   int last_launches;
@@ -812,13 +810,16 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
     for (int b = 0; b < desc->nbox; b++)
       dc.box_rbound[b] = sqrtf(desc->box_size[b][0] * desc->box_size[b][0] + desc->box_size[b][1] * desc->box_size[b][1] + desc->box_size[b][2] * desc->box_size[b][2]);
   }
-  m->d_desc = nullptr; m->d_cfg = nullptr; m->d_derived = nullptr;
-  e = cudaMalloc(&m->d_desc, sizeof(PupperModelDesc));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_cfg, sizeof(PupperEnvCfg));
-  if (e == cudaSuccess) e = cudaMalloc(&m->d_derived, sizeof(pupper::DerivedConsts));
-  if (e == cudaSuccess) e = cudaMemcpy(m->d_desc, desc, sizeof(PupperModelDesc), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(m->d_cfg, cfg, sizeof(PupperEnvCfg), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(m->d_derived, &dc, sizeof(dc), cudaMemcpyHostToDevice);
+  m->d_consts = nullptr;
+  {
+    pupper::ConstBlock *hb = new (std::nothrow) pupper::ConstBlock();
+    if (!hb) { delete m; return PUPPER_ENOMEM; }
+    memset(hb, 0, sizeof(*hb));
+    hb->m = *desc; hb->c = *cfg; hb->d = dc;
+    e = cudaMalloc(&m->d_consts, sizeof(pupper::ConstBlock));
+    if (e == cudaSuccess) e = cudaMemcpy(m->d_consts, hb, sizeof(pupper::ConstBlock), cudaMemcpyHostToDevice);
+    delete hb;
+  }
   int smem = (int)sizeof(pupper::BlockShared);
   if (const char *pad = getenv("PUPPER_EXTRA_SMEM")) smem += atoi(pad);
   m->smem_bytes = smem;
@@ -826,7 +827,7 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(pupper::env_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e != cudaSuccess) { cudaFree(m->d_desc); cudaFree(m->d_cfg); cudaFree(m->d_derived); delete m; return cuda_fail(e, "pupper_model_create"); }
+  if (e != cudaSuccess) { cudaFree(m->d_consts); delete m; return cuda_fail(e, "pupper_model_create"); }
   *out = m;
   return PUPPER_OK;
 }
@@ -834,9 +835,7 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
 int pupper_model_destroy(PupperModel *m) {
   if (!m) return PUPPER_EINVAL;
   cudaSetDevice(m->device);
-  cudaFree(m->d_desc);
-  cudaFree(m->d_cfg);
-  cudaFree(m->d_derived);
+  cudaFree(m->d_consts);
   delete m;
   return PUPPER_OK;
 }
@@ -860,9 +859,7 @@ static pupper::KParams make_params(const PupperModel *model, int n_envs, const P
                                    const uint32_t *keys, const PupperStepOut *out, const PupperEpisode *ep, const PupperRand *rand) {
   pupper::KParams p;
   memset(&p, 0, sizeof(p));
-  p.model = model->d_desc;
-  p.cfg = model->d_cfg;
-  p.derived = model->d_derived;
+  p.consts = model->d_consts;
   p.n_envs = n_envs;
   p.st = *st;
   if (dr) { p.dr = *dr; p.has_dr = 1; }

@@ -49,11 +49,9 @@ constexpr int kMaxCon = 5;            // contact slots per env (max_contact_poin
 constexpr float kMinVal = 1e-15f, kMinImp = 1e-4f, kMaxImp = 0.9999f;
 constexpr float kInf = 3.0e38f;
 
-struct DerivedConsts;
+struct ConstBlock;
 struct KParams {
-  const PupperModelDesc *model;  // device copies
-  const PupperEnvCfg *cfg;
-  const DerivedConsts *derived;
+  const ConstBlock *consts;  // device copy of the model description, env configuration and derived constants (one block)
   int n_envs;
   PupperState st;
   PupperDR dr;
@@ -101,10 +99,16 @@ struct DerivedConsts {  // computed once on the host in pupper_model_create
   int ss_pair[24];             // leg-leg sphere pairs in MJX order: a | b << 8  ({(a,b): a<b, a/2 != b/2}, lexicographic)
 };
 
-struct BlockShared {
+// Everything the kernel reads that is constant for a model: one device block, copied to the head of each CTA's shared memory
+// in 16-byte pieces (pupper_model_create builds it).
+struct alignas(16) ConstBlock {
   PupperModelDesc m;
   PupperEnvCfg c;
   DerivedConsts d;
+};
+static_assert(sizeof(ConstBlock) % 16 == 0, "ConstBlock is copied in 16-byte pieces");
+
+struct BlockShared : ConstBlock {
   EnvShared env[kEnvsPerBlock];
   float rows[3 * kMaxCon * kBlock];  // contact-edge row scalars: [buffer][contact][thread]
   float4 lsf[6 * kBlock];            // line search, per friction-loss row j: [2j] (Jaref, jv, R f, qc), [2j+1] linear-zone corrections
