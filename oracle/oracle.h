@@ -120,6 +120,12 @@ int oracle_reset_ext_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int 
 int oracle_step_ext_f32(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, const OracleDR *dr,
                         OracleEnv *envs, const double *action, int episode, OracleDebug *dbg, int n_threads, const float *ext_u);
 
+/* Physics only, one env (n_frames <= 0: pipeline_init = one forward pass; else n_frames x mjx.step); see pupper_oracle.c */
+int oracle_pipeline_f64(const PupperModelDesc *m, const OracleDR *dr, int n_frames, double *qpos, double *qvel, double *warm,
+                        const double *ctrl, OracleDebug *dbg);
+int oracle_pipeline_f32(const PupperModelDesc *m, const OracleDR *dr, int n_frames, double *qpos, double *qvel, double *warm,
+                        const double *ctrl, OracleDebug *dbg);
+
 /* PRNG known-answer access (jax 0.5.0 threefry, partitionable). */
 void oracle_threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t *out);
 float oracle_uniform(uint32_t k0, uint32_t k1, uint32_t index, float lo, float hi);

@@ -155,6 +155,20 @@ class Oracle:
         return self.envs[name][:, : rows * L].reshape(-1, rows, L)
 
 
+def pipeline(model_desc, qpos, qvel, warm, ctrl, n_frames: int, precision: str = "f32", dr: Optional[np.ndarray] = None):
+    """Physics only for one env: n_frames <= 0 is Brax's pipeline_init (one forward pass), else pipeline_step.
+    Returns (qpos, qvel, qacc_warmstart, debug record)."""
+    q = np.array(qpos, dtype=np.float64).reshape(19).copy()
+    v = np.array(qvel, dtype=np.float64).reshape(18).copy()
+    w = np.array(warm, dtype=np.float64).reshape(18).copy()
+    c = np.ascontiguousarray(ctrl, dtype=np.float64).reshape(NU)
+    dbg = np.zeros(1, dtype=DEBUG_DTYPE)
+    drr = None if dr is None else np.ascontiguousarray(dr, dtype=DR_DTYPE).reshape(1)
+    rc = getattr(lib(), f"oracle_pipeline_{precision}")(C.byref(model_desc), _ptr(drr), int(n_frames), _ptr(q), _ptr(v), _ptr(w), _ptr(c), _ptr(dbg))
+    assert rc == 0, rc
+    return q, v, w, dbg[0]
+
+
 def threefry2x32(k0, k1, c0, c1):
     out = (C.c_uint32 * 2)()
     lib().oracle_threefry2x32(k0, k1, c0, c1, out)

@@ -1386,3 +1386,34 @@ int SUF(oracle_step)(const PupperModelDesc *m, const PupperEnvCfg *cfg, int n, c
                      const double *action, int episode, OracleDebug *dbg, int n_threads) {
   return SUF(oracle_step_ext)(m, cfg, n, dr, envs, action, episode, dbg, n_threads, NULL);
 }
+
+/* Physics only, one env: what the reference reaches through Brax -- pipeline_init (n_frames <= 0: one forward pass, the
+ * warm start becomes its qacc) and pipeline_step (n_frames x mjx.step; environment.py:319,366) -- so that the reference's own
+ * env-level code can be run with the oracle's physics underneath (tests/refshim).  In/out: qpos[19], qvel[18], warm[18]. */
+int SUF(oracle_pipeline)(const PupperModelDesc *m, const OracleDR *dr, int n_frames, double *qpos, double *qvel, double *warm,
+                         const double *ctrl_in, OracleDebug *dbg) {
+  if (!m || !qpos || !qvel || !warm || !ctrl_in) return -1;
+  Model M;
+  Data D;
+  BraxX X;
+  model_load(&M, m, dr);
+  real q[NQ], v[NV], w[NV], ctrl[NU];
+  for (int i = 0; i < NQ; i++) q[i] = (real)qpos[i];
+  for (int i = 0; i < NV; i++) { v[i] = (real)qvel[i]; w[i] = (real)warm[i]; }
+  for (int i = 0; i < NU; i++) ctrl[i] = (real)ctrl_in[i];
+  if (n_frames <= 0) {
+    forward(&M, &D, q, v, ctrl, w);
+    for (int d = 0; d < NV; d++) w[d] = D.qacc[d];
+  } else {
+    for (int f = 0; f < n_frames; f++) {
+      forward(&M, &D, q, v, ctrl, w);
+      for (int d = 0; d < NV; d++) w[d] = D.qacc[d];
+      euler(&M, &D, q, v);
+    }
+  }
+  brax_x_xd(&D, &X);
+  if (dbg) { memset(dbg, 0, sizeof(*dbg)); debug_fill(&D, &X, dbg); }
+  for (int i = 0; i < NQ; i++) qpos[i] = (double)q[i];
+  for (int i = 0; i < NV; i++) { qvel[i] = (double)v[i]; warm[i] = (double)w[i]; }
+  return 0;
+}
