@@ -6,9 +6,12 @@
  * domain_randomization.py:188-210) including the third-party physics that path delegates to
  * (mujoco_mjx==3.2.7 mjx.step, brax==0.12.1 mjx pipeline, jax==0.5.0 threefry PRNG; none of them is
  * vendored in the reference nor installable here -- their published algorithms are restated, see
- * SURVEY.md Appendix A).  PARITY UNPINNED: the reference's own tests hold no physics golden vectors
- * and the reference cannot be run in this image, so the oracle is checked against the reference's
- * known-answer tests for the lag buffers / PRNG and against physics invariants only.
+ * SURVEY.md Appendix A).
+ * PARITY STATUS: the env level (everything the reference itself implements on the path) is PINNED against the
+ * reference's own code executed in the build container (tests/refshim + tests/golden/make_ref_golden.py ->
+ * tests/golden/ref_*.npz, checked step by step by tests/test_ref_golden.py); the third-party physics under it is
+ * UNPINNED against MJX (no installable MJX, no physics goldens in the reference) and is checked by physics invariants,
+ * closed forms and known-answer tests only.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.

@@ -10,7 +10,7 @@
  *                 jax==0.5.0 threefry PRNG -- un-vendored pins (requirements.txt:1-5); the published
  *                 algorithms are restated as specified in SURVEY.md Appendix A, dense and in MJX's
  *                 evaluation order (no sparsity tricks; those belong to the CUDA kernel under test).
- * PARITY UNPINNED: see oracle.h.
+ * PARITY STATUS: env level pinned against the reference executed under tests/refshim, physics [3P] unpinned against MJX -- see oracle.h.
  *
  * Compiled twice (REAL=double -> *_f64, REAL=float -> *_f32) with -ffp-contract=off.
  */
