@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PUPPER_ABI_VERSION 2
+#define PUPPER_ABI_VERSION 3
 
 /* Fixed topology of the supported robot family: world + base + 4 legs x 3 links. */
 #define PUPPER_NBODY 14
@@ -47,6 +47,7 @@ extern "C" {
 #define PUPPER_KERNEL_MAX_PAIRS 4 /* and 1 <= max_geom_pairs <= 4 (one narrow phase per lane of the env's quad); the
                                      reference model sets 5 / 4 (test_pupper_model.xml:227-230); MJX's -1 = "no limit" is
                                      outside the supported family (pupper_model_create: PUPPER_EUNSUPPORTED) */
+#define PUPPER_NEFC_TAP 44 /* rows of PupperStepOut.dbg_efc */
 #define PUPPER_NRAND 44    /* uniform draws one reset / step consumes per env (PupperRand) */
 #define PUPPER_MAX_LAT 8   /* longest latency distribution (action and IMU) */
 #define PUPPER_NREWARD 18
@@ -250,6 +251,13 @@ typedef struct PupperStepOut {
    *   [6] the accepted step size alpha (float bits)
    *   [7] number of leg-leg contacts among [2] */
   int32_t *dbg_solver;   /* [n_envs][8] */
+  /* constraint rows of the last substep as the solver saw them: (efc_D, efc_aref) per row, rows in the order
+   *   0-11  friction-loss rows of the 12 hinge dofs,
+   *   12-23 joint-limit rows of the 12 hinges (D = 0: limit not violated, no row),
+   *   24-43 pyramid edges: 4 per contact slot (n + mu t1, n - mu t1, n + mu t2, n - mu t2), slots as in dbg_contact_*
+   *         (D = 0 past the active contacts)
+   * (oracle: OracleDebug.efc_D / efc_aref; mjx constraint.py make_constraint) */
+  float *dbg_efc;        /* [n_envs][44][2] */
 } PupperStepOut;
 
 /* External randoms (optional; NULL = every draw is made in-kernel with threefry2x32 from state->rng).

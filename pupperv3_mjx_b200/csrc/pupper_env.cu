@@ -461,6 +461,15 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     if (p.out.dbg_solver && !RESET && k == 0) {
       for (int i = 0; i < 8; i++) if (valid) p.out.dbg_solver[(size_t)e * 8 + i] = dbg.solver[i];
     }
+    if (p.out.dbg_efc && !RESET) {
+      float *o = p.out.dbg_efc + (size_t)e * (PUPPER_NEFC_TAP * 2);
+      for (int j = 0; j < 3; j++) {
+        const int r = 3 * k + j;
+        if (valid) { o[2 * r] = dbg.efc_fD[j]; o[2 * r + 1] = dbg.efc_fA[j]; o[2 * (12 + r)] = dbg.efc_lD[j]; o[2 * (12 + r) + 1] = dbg.efc_lA[j]; }
+      }
+      for (int c = 0; c < kMaxCon; c++)
+        if (valid) { o[2 * (24 + 4 * c + k)] = dbg.efc_cD[c]; o[2 * (24 + 4 * c + k) + 1] = dbg.efc_cA[c]; }
+    }
     if (p.out.dbg_site_xpos) {
       float *o = p.out.dbg_site_xpos + (size_t)e * 15;
       if (valid) o[3 + 3 * k] = so.foot_site.x; if (valid) o[4 + 3 * k] = so.foot_site.y; if (valid) o[5 + 3 * k] = so.foot_site.z;
@@ -876,7 +885,7 @@ static pupper::KParams make_params(const PupperModel *model, int n_envs, const P
 }
 
 static bool wants_debug(const PupperStepOut *o) {
-  return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc || o->dbg_solver;
+  return o->dbg_x_pos || o->dbg_qfrc_actuator || o->dbg_contact_dist || o->dbg_site_xpos || o->dbg_qacc || o->dbg_solver || o->dbg_efc;
 }
 // the x / xd taps come as a group, and so do the two contact taps
 static bool debug_ok(const PupperStepOut *o) {

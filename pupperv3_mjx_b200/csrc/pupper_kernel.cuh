@@ -517,6 +517,8 @@ struct DbgOut {  // only filled when DBG
   V3 pos[3]; Q4 rot[3]; V3 ang[3], vel[3];
   float qacc_b[6], qacc_l[3];
   int solver[8];  // PupperStepOut.dbg_solver (replicated over the quad)
+  // PupperStepOut.dbg_efc, this lane's rows: friction-loss / limit rows of its 3 hinges, its pyramid edge of every slot
+  float efc_fD[3], efc_fA[3], efc_lD[3], efc_lA[3], efc_cD[kMaxCon], efc_cA[kMaxCon];
 };
 
 __device__ __forceinline__ StaleOut load_stale(const EnvShared &es, int k) {
@@ -572,7 +574,7 @@ __device__ __forceinline__ void link2_velocity(const S6 cd[3], const V3 ba[3], c
 // COST (N == 3, vectors = qvel, warm start, qacc_smooth): rows 1 and 2 are stored as Jaref = J.x - aref (buffers B, C)
 // and the constraint cost at both start points is accumulated in cw / cs; row 0 only feeds aref.
 // !COST (N == 1): the row is stored in buffer A.
-template <int N, bool COST>
+template <int N, bool COST, bool TAP = false>
 __device__ __forceinline__ void contact_rows_own(const EnvShared &es, const S6 cd[3], const V3 ba[3], const V3 bo[3], const float (&vb)[N][6],
                                                  const float (&vl)[N][3], int own_list, int own_count, int nown_w, int part_all, float *out,
                                                  float &cw, float &cs) {
@@ -606,6 +608,7 @@ __device__ __forceinline__ void contact_rows_own(const EnvShared &es, const S6 c
         for (int e = 0; e < 4; e++) {
           const float aref = -b * row[0][e] - kimp;
           const float xw = row[N > 1 ? 1 : 0][e] - aref, xs = row[N > 2 ? 2 : 0][e] - aref;
+          if (TAP) o[e] = aref;  // debug instantiation: buffer A (unused until the line search) carries aref to the dbg_efc tap
           o[kMaxCon * kBlock + e] = xw; o[2 * kMaxCon * kBlock + e] = xs;  // Jaref at the warm start / at qacc_smooth
           const float mw = fminf(xw, 0.f), ms = fminf(xs, 0.f);
           cw = fmaf(hD * mw, mw, cw);
@@ -1515,7 +1518,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int j = 0; j < 3; j++) { v3l[0][j] = L.vl[j]; v3l[1][j] = L.wl[j]; v3l[2][j] = sl[j]; }
     // contact rows at qvel / warm start / qacc_smooth, their reference accelerations and both start costs: world-vs-leg
     // contacts by the touching leg's lane (all four edges), leg-leg contacts edge by edge with a sum over the quad
-    contact_rows_own<3, true>(es, cd, ba, bo, v3b, v3l, own_list, own_count, nown_w, part_all, rowQ, cw_con, cs_con);
+    contact_rows_own<3, true, DBG>(es, cd, ba, bo, v3b, v3l, own_list, own_count, nown_w, part_all, rowQ, cw_con, cs_con);
     if (ss_mask_w) {  // leg-leg contact somewhere in the warp (rare): out of line, arguments through memory
       LegLegIO<3> io;
 #pragma unroll
@@ -1558,6 +1561,18 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       cw += dc.x; cs += dc.y;
     }
     __syncwarp(qm);  // Jaref rows written by the owning lanes are visible to every edge's lane
+    if (DBG && want_stale && dbg) {  // constraint rows as the solver sees them (PupperStepOut.dbg_efc)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { dbg->efc_fD[j] = fl[j] > 0.f ? fD[j] : 0.f; dbg->efc_fA[j] = fA[j]; dbg->efc_lD[j] = lD[j]; dbg->efc_lA[j] = lA[j]; }
+#pragma unroll
+      for (int c = 0; c < kMaxCon; c++) {
+        const bool on = c < ncon;
+        const bool is_ss = on && es.con[c].code1 >= 0 && es.con[c].code2 >= 0;
+        dbg->efc_cD[c] = on ? es.con[c].D : 0.f;
+        // own contacts: aref parked in buffer A by contact_rows_own; leg-leg slots: buffer A holds J.qvel of this lane's edge
+        dbg->efc_cA[c] = on ? (is_ss ? -es.con[c].b * rowA[c * kBlock] - es.con[c].kimp : rowA[c * kBlock]) : 0.f;
+      }
+    }
     float gw = 0.f;
 #pragma unroll
     for (int j = 0; j < 3; j++) gw = fmaf(Maw_l[j] - fs_l[j], L.wl[j] - sl[j], gw);

@@ -195,7 +195,7 @@ class EnvRuntime:
             mc = model_desc.max_contact_points
             shapes = {"dbg_x_pos": (13, 3), "dbg_x_rot": (13, 4), "dbg_xd_vel": (13, 3), "dbg_xd_ang": (13, 3),
                       "dbg_qfrc_actuator": (18,), "dbg_contact_dist": (mc,), "dbg_contact_geom": (mc, 2),
-                      "dbg_site_xpos": (5, 3), "dbg_qacc": (18,), "dbg_solver": (8,)}
+                      "dbg_site_xpos": (5, 3), "dbg_qacc": (18,), "dbg_solver": (8,), "dbg_efc": (44, 2)}
             for name, shp in shapes.items():
                 dt = torch.int32 if name in ("dbg_contact_geom", "dbg_solver") else torch.float32
                 t = torch.zeros((self.n_envs,) + shp, dtype=dt, device=self.device)

@@ -93,6 +93,56 @@ def test_single_substep_smooth_quantities_and_contact_sets():
         np.testing.assert_array_equal(h.get("last_act"), O.envs["last_act"].astype(np.float32))
 
 
+def test_constraint_rows_single_substep():
+    """P5 (make_constraint): efc_D and efc_aref of every row the solver sees -- 12 friction-loss rows, the violated joint-limit
+    rows, 4 pyramid edges per active contact -- from the kernel's `dbg_efc` tap against the float64 oracle, on EXACTLY the
+    injected state (n_frames = 1).  Contacts are matched by geom pair (slot order may differ from the oracle's)."""
+    env = common.make_env(environment_timestep=0.004)
+    full = common.make_env()
+    n = 128
+    h, O, _ = _pair(env, n, debug=True)
+    roll = oracle.Oracle(full.model_desc, full.env_cfg, "f64")
+    roll.reset(common.env_keys(n)); O.reset(common.env_keys(n)); h.reset(common.env_keys(n))
+    seen = {"friction": 0, "limit": 0, "contact": 0}
+    worst = {"D": 0.0, "aref": 0.0}
+    def close(a, b, what):
+        err = np.abs(a - b) / (1e-3 + np.abs(b).max())   # a row group's aref terms cancel: measure against the group's scale
+        worst[what] = max(worst[what], float(err.max()) if err.size else 0.0)
+        return (err < (2e-4 if what == "D" else 2e-3)).all()
+    for t in range(40):
+        a = common.actions(n, t, scale=1.0 if t % 3 == 0 else 0.5)   # full-range actions push joints into their limits
+        O.envs = roll.envs.copy()
+        h.load_state(roll.envs)
+        O.step(a, debug=True); h.step(a); roll.step(a)
+        d = O.debug
+        tap = h.rt.dbg["dbg_efc"].cpu().numpy().reshape(n, 44, 2)
+        cd, cg = h.rt.dbg["dbg_contact_dist"].cpu().numpy(), h.rt.dbg["dbg_contact_geom"].cpu().numpy()
+        for i in range(n):
+            nf = 12
+            assert close(tap[i, :12, 0], d["efc_D"][i, :nf], "D") and close(tap[i, :12, 1], d["efc_aref"][i, :nf], "aref"), (t, i, "friction")
+            seen["friction"] += 12
+            for j in range(12):
+                r = nf + j
+                if d["efc_pos"][i, r] < 0:
+                    assert tap[i, 12 + j, 0] > 0, (t, i, j, "limit row missing")
+                    assert close(tap[i, 12 + j, :1], d["efc_D"][i, r:r + 1], "D") and close(tap[i, 12 + j, 1:], d["efc_aref"][i, r:r + 1], "aref"), (t, i, j, "limit")
+                    seen["limit"] += 1
+                else:
+                    assert tap[i, 12 + j, 0] == 0
+            slots = {(int(cg[i, c, 0]), int(cg[i, c, 1])): c for c in range(cd.shape[1]) if cd[i, c] < 0}
+            for c in range(int(d["ncon"][i])):
+                if d["contact_dist"][i, c] >= -1e-6:
+                    continue  # (a contact within rounding of zero penetration may exist on one side only)
+                g = (int(d["contact_geom"][i, c, 0]), int(d["contact_geom"][i, c, 1]))
+                assert g in slots, (t, i, g)
+                r0, k0 = nf + 12 + 4 * c, 24 + 4 * slots[g]
+                assert close(tap[i, k0:k0 + 4, 0], d["efc_D"][i, r0:r0 + 4], "D"), (t, i, g, tap[i, k0:k0 + 4, 0], d["efc_D"][i, r0:r0 + 4])
+                assert close(tap[i, k0:k0 + 4, 1], d["efc_aref"][i, r0:r0 + 4], "aref"), (t, i, g, tap[i, k0:k0 + 4, 1], d["efc_aref"][i, r0:r0 + 4])
+                seen["contact"] += 4
+    print("rows compared", seen, "worst relative error", worst)
+    assert seen["limit"] >= 10 and seen["contact"] > 5000
+
+
 def _stat_parity(env, n, T, dr_sys=None, episode=False, min_quiet=None):
     h, O, O32 = _pair(env, n, episode=episode, dr=dr_sys)
     roll = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
