@@ -31,6 +31,14 @@ namespace pupper {
 #define PUPPER_PHASE_SYNC 1
 #endif
 // A/B switches of individual optimisations (tools/jobs/ab.sh builds the variants and times them on one box)
+#ifndef PUPPER_FAST_ROT
+#define PUPPER_FAST_ROT 1  // kinematics: the 15-instruction form of the quaternion rotation (pupper_math.cuh rotate_fast)
+#endif
+#if PUPPER_FAST_ROT
+#define KROT rotate_fast
+#else
+#define KROT rotate
+#endif
 #ifndef PUPPER_ZFOLD
 #define PUPPER_ZFOLD 1   // structural zeros folded by hand (the compiler may not drop 0*x terms)
 #endif
@@ -1126,7 +1134,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const int b = b0 + j;
-      pos[j] = pp + rotate(V3{m.body_pos[b][0], m.body_pos[b][1], m.body_pos[b][2]}, pq);
+      pos[j] = pp + KROT(V3{m.body_pos[b][0], m.body_pos[b][1], m.body_pos[b][2]}, pq);
       Q4 q = qmul(pq, Q4{m.body_quat[b][0], m.body_quat[b][1], m.body_quat[b][2], m.body_quat[b][3]});
       float sn, cs;
       sincos_small(L.ql[j] * 0.5f, &sn, &cs);
@@ -1134,10 +1142,10 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
       axis[j] = rotate_z(q);
       rot[j] = qmul_zrot(q, cs, sn);
 #else
-      axis[j] = rotate(V3{0.f, 0.f, 1.f}, q);
+      axis[j] = KROT(V3{0.f, 0.f, 1.f}, q);
       rot[j] = qmul(q, Q4{cs, 0.f, 0.f, sn});
 #endif
-      xip[j] = pos[j] + rotate(V3{m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]}, rot[j]);
+      xip[j] = pos[j] + KROT(V3{m.body_ipos[b][0], m.body_ipos[b][1], m.body_ipos[b][2]}, rot[j]);
       M3 Ri = qmat(qmul(rot[j], Q4{m.body_iquat[b][0], m.body_iquat[b][1], m.body_iquat[b][2], m.body_iquat[b][3]}));
       const float *di = &es.inertia[(b - 1) * 3];
       Iw[j][0] = Ri.m[0] * di[0] * Ri.m[0] + Ri.m[1] * di[1] * Ri.m[1] + Ri.m[2] * di[2] * Ri.m[2];
@@ -1152,12 +1160,12 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   }
   // collision sphere centres (knee on link2, foot on link3) and the foot site
   V3 sc[2];
-  sc[0] = pos[1] + rotate(V3{m.sphere_pos[2 * k][0], m.sphere_pos[2 * k][1], m.sphere_pos[2 * k][2]}, rot[1]);
-  sc[1] = pos[2] + rotate(V3{m.sphere_pos[2 * k + 1][0], m.sphere_pos[2 * k + 1][1], m.sphere_pos[2 * k + 1][2]}, rot[2]);
+  sc[0] = pos[1] + KROT(V3{m.sphere_pos[2 * k][0], m.sphere_pos[2 * k][1], m.sphere_pos[2 * k][2]}, rot[1]);
+  sc[1] = pos[2] + KROT(V3{m.sphere_pos[2 * k + 1][0], m.sphere_pos[2 * k + 1][1], m.sphere_pos[2 * k + 1][2]}, rot[2]);
   es.sph[2 * k][0] = sc[0].x; es.sph[2 * k][1] = sc[0].y; es.sph[2 * k][2] = sc[0].z;
   es.sph[2 * k + 1][0] = sc[1].x; es.sph[2 * k + 1][1] = sc[1].y; es.sph[2 * k + 1][2] = sc[1].z;
   // base inertial frame
-  const V3 xip_b = p1 + rotate(V3{es.ipos[0], es.ipos[1], es.ipos[2]}, q1);
+  const V3 xip_b = p1 + KROT(V3{es.ipos[0], es.ipos[1], es.ipos[2]}, q1);
   float Iwb[6];
   {
     M3 Ri = qmat(qmul(q1, Q4{m.body_iquat[1][0], m.body_iquat[1][1], m.body_iquat[1][2], m.body_iquat[1][3]}));
