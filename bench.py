@@ -296,6 +296,18 @@ def run_cuda(args):
                 "value": 16384 / (float(np.mean(ps)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ps)), "envs": 16384, "steps": xs,
                 "note": "10-box obstacles.py terrain, kicks on, full DR, same timing loop"}
             del r2, a2
+        if world == 1:
+            # one run whose state genuinely streams from HBM (H = 15: 5,596 + 192 B per env-step, 380 MB per step)
+            env_h = common.make_env(observation_history=15)
+            env_h.set_episode_params(1000, 1)
+            r2, a2 = make_runtime(env_h, 65536)
+            ps, _, _, _ = timed_steps(r2, a2, 30, 3, 20, True)
+            bh = b_alg(15) * 65536
+            configs["65,536 envs with observation_history = 15 (HBM-streaming variant)"] = {
+                "value": 65536 / (float(np.mean(ps)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(ps)), "envs": 65536, "steps": 30,
+                "algorithmic_GB_per_s": bh / (float(np.mean(ps)) * 1e-3) / 1e9,
+                "note": "flat ground, full DR; the obs history alone is 283 MB per step, beyond the 126 MB L2"}
+            del r2, a2
         # configs[4]: rollout collection with the policy MLP in the loop, 8192 envs per GPU (x N GPUs)
         import functools
         from pupperv3_mjx_b200 import rollout, wrappers
