@@ -370,15 +370,23 @@ class EnvRuntime:
             self._d_act = torch.empty((n, abi.NU), dtype=torch.float32, device=self.device)
             self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
             self._done_ev = torch.cuda.Event()
+            self._zero_copy_action = os.environ.get("PUPPER_HOST_ACTION_COPY", "0") != "1"
         cur = torch.cuda.current_stream(self.device)
         if chunks <= 1:
             # latency path: three enqueues on the caller's stream; the stream itself is the thing to wait on
             if torch.cuda.current_device() != self.device_index:  # rare: the caller works on another device
                 with torch.cuda.device(self.device):
                     return self.step_host(h_action, h_out, chunks)
-            self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
+            # Pinned host memory is device-addressable under unified addressing: the kernel reads the 48 bytes per env
+            # straight from h_action over PCIe (one ~2 us round trip inside its prologue) instead of waiting for a
+            # separate H2D copy (launch + transfer ahead of the kernel); PUPPER_HOST_ACTION_COPY=1 restores the copy.
+            if self._zero_copy_action:
+                act_ptr = h_action.data_ptr()
+            else:
+                self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
+                act_ptr = self._d_act.data_ptr()
             rc = self.lib.pupper_step(self._model, n, C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
-                                      self._d_act.data_ptr(), None, C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                      act_ptr, None, C.byref(self.out), C.byref(self.episode) if self.episode else None,
                                       cur.cuda_stream)
             if rc != 0:
                 _check(self.lib, rc, "pupper_step")
