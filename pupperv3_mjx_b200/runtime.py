@@ -289,7 +289,9 @@ class EnvRuntime:
         _check(self.lib, rc, "pupper_reset")
         self.launches += self.lib.pupper_last_launch_count(self._model)
 
-    def step(self, action: torch.Tensor, ext_rand: Optional[torch.Tensor] = None):
+    def step(self, action: torch.Tensor, ext_rand: Optional[torch.Tensor] = None, with_episode: bool = True):
+        """One env step.  ``with_episode=False`` runs the bare env step even when the fused Episode / AutoReset block is
+        allocated (the inner steps of an ``action_repeat`` > 1 wrapper step)."""
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
                 or action.numel() != self.n_envs * abi.NU:
             raise PupperError("action must be a contiguous float32 CUDA tensor of shape [n_envs, 12] on the env's device")
@@ -297,7 +299,7 @@ class EnvRuntime:
         with torch.cuda.device(self.device):
             rc = self.lib.pupper_step(self._model, self.n_envs, C.byref(self._dr_struct) if self._dr_struct else None,
                                       C.byref(self.state), action.data_ptr(), C.byref(rand) if rand is not None else None,
-                                      C.byref(self.out), C.byref(self.episode) if self.episode else None, self._stream())
+                                      C.byref(self.out), C.byref(self.episode) if (self.episode and with_episode) else None, self._stream())
         _check(self.lib, rc, "pupper_step")
         self.launches += 1
 

@@ -19,8 +19,8 @@ class TrainingEnv:
 
     def __init__(self, env: PupperV3Env, episode_length: int = 1000, action_repeat: int = 1,
                  randomization_fn: Optional[Callable] = None):
-        if action_repeat != 1:
-            raise NotImplementedError("the fused EpisodeWrapper supports action_repeat=1 (the reference's training setting)")
+        if action_repeat < 1:
+            raise ValueError("action_repeat must be >= 1")
         self.env = env
         self.episode_length, self.action_repeat = int(episode_length), int(action_repeat)
         env.set_episode_params(episode_length, action_repeat)
@@ -69,8 +69,25 @@ class TrainingEnv:
         return self.env._state_from_runtime(rt)
 
     def step(self, state: State, action) -> State:
+        """Brax EpisodeWrapper.step + AutoResetWrapper.step.  ``action_repeat`` = 1 (the reference's training setting) is one
+        fused launch.  For R > 1 Brax scans ``env.step`` R times with the same action, sums the rewards and does its
+        episode accounting once on the last state: here R - 1 bare env steps, then the fused step (which adds R to
+        ``steps`` / ``length`` and accounts the last step's reward and metrics), then the earlier rewards are added to the
+        reward, to ``episode_metrics["sum_reward"]`` and to the completed-episode accumulator."""
         rt = state.pipeline_state.runtime
+        if self.action_repeat == 1:
+            rt.step(action)
+            return self.env._state_from_runtime(rt)
+        partial = None
+        for _ in range(self.action_repeat - 1):
+            rt.step(action, with_episode=False)
+            partial = rt.reward.clone() if partial is None else partial + rt.reward
+        keep = (rt.episode_field("episode_done")[0] == 0).to(partial.dtype)   # episodes that were live before this step
         rt.step(action)
+        rt.reward.add_(partial)                       # state.reward = sum over the R inner steps
+        partial = partial * keep                      # episode metrics restart where the previous step ended an episode
+        rt.episode_field("sum_reward")[0].add_(partial)
+        rt.episode_field("totals")[1].add_((partial * rt.done).sum())
         return self.env._state_from_runtime(rt)
 
     def episode_totals(self):

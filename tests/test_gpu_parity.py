@@ -325,6 +325,58 @@ def test_episode_and_autoreset_fused():
     assert tot[0] >= 2 * n and tot[2] > 0
 
 
+def test_action_repeat_follows_the_brax_episode_wrapper():
+    """wrappers.wrap(..., action_repeat=2): Brax's EpisodeWrapper scans env.step twice with the same action, sums the rewards,
+    adds 2 to steps / length and accounts on the last state; AutoResetWrapper restores the first state where done.  The wrapper
+    logic is restated here in NumPy over the oracle's BARE env step and compared from identical states every wrapper step."""
+    import torch
+    from pupperv3_mjx_b200 import wrappers
+    R, Lmax, n = 2, 9, 64
+    env = common.make_env()
+    tenv = wrappers.wrap(env, episode_length=Lmax, action_repeat=R)
+    keys = common.env_keys(n)
+    st = tenv.reset(torch.from_numpy(np.ascontiguousarray(keys).view(np.int32)).cuda())
+    h = Harness.__new__(Harness)
+    h.env, h.n, h.rt, h.cfg = env, n, tenv._rt, env.env_cfg
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f64")
+    O.reset(keys)
+    steps = np.zeros(n, np.int64); ep_done = np.zeros(n); sum_reward = np.zeros(n); length = np.zeros(n)
+    finished = 0
+    for t in range(14):
+        a = common.actions(n, t)
+        O.envs = h.dump_state()
+        rsum = np.zeros(n)
+        for _ in range(R):
+            O.step(a, episode=False)
+            rsum += O.envs["reward"]
+        done = O.envs["done"].copy()
+        steps = np.where(ep_done != 0, 0, steps) + R
+        trunc = steps >= Lmax
+        done2 = np.where(trunc, 1.0, done)
+        truncation = np.where(trunc, 1.0 - done, 0.0)
+        keep = 1.0 - ep_done
+        sum_reward = (sum_reward + rsum) * keep
+        length = (length + R) * keep
+        ep_done = done2
+        st = tenv.step(st, torch.from_numpy(a).cuda())
+        torch.cuda.synchronize()
+        ok = h.get("done") == done2
+        assert ok.mean() > 0.97
+        assert np.array_equal(h.get("steps")[ok], steps[ok])
+        np.testing.assert_array_equal(h.get("truncation")[ok], truncation[ok])
+        np.testing.assert_allclose(h.get("length")[ok], length[ok])
+        assert np.median(np.abs(h.get("reward") - rsum)) < 2e-5 and np.median(np.abs(h.get("sum_reward") - sum_reward)) < 4e-5
+        dn = (done2 == 1) & ok
+        finished += int(dn.sum())
+        np.testing.assert_array_equal(h.get("qpos")[dn], h.get("first_qpos")[dn])
+        # a flag that differs (solver discreteness) desynchronises that env's wrapper state: follow the CUDA side from here
+        steps, ep_done = h.get("steps").astype(np.int64), h.get("episode_done").astype(np.float64)
+        sum_reward, length = h.get("sum_reward").astype(np.float64), h.get("length").astype(np.float64)
+    assert finished >= 2 * n   # truncation at 9 steps = every 5th wrapper step, plus falls
+    tot = h.rt.episode_field("totals").cpu().numpy()
+    assert tot[0] >= 2 * n and tot[2] % R == 0 and Lmax - 1 - R <= tot[2] / tot[0] <= Lmax + R   # lengths advance by R
+
+
 def test_command_resampling_is_exact():
     env = common.make_env(resample_velocity_step=3, zero_command_probability=0.3)
     n = 64
