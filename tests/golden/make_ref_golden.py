@@ -106,6 +106,15 @@ def main():
                                    "dones": int(data["done"].sum()), "kicks": int((np.abs(data["info_kick"]).sum(-1) > 0).sum())}
             print(name, {k: v.shape for k, v in list(data.items())[:3]}, meta["cases"][name])
 
+    # ---- what the constructor derives from the model (environment.py:165-244): ids, start pose, time steps ------------------
+    env = environment.PupperV3Env(**ref_kwargs())
+    meta["ctor"] = {"init_q": np.asarray(env._init_q).tolist(), "torso_idx": int(env._torso_idx), "feet_site_id": np.asarray(env._feet_site_id).tolist(),
+                    "lower_leg_body_id": np.asarray(env._lower_leg_body_id).tolist(), "upper_leg_geom_ids": np.asarray(env._upper_leg_geom_ids).tolist(),
+                    "torso_geom_ids": np.asarray(env._torso_geom_ids).tolist(), "dt": float(env.dt), "n_frames": int(env._n_frames), "nv": int(env._nv),
+                    "kp": np.asarray(env.sys.actuator_gainprm)[:, 0].tolist(), "bias1": np.asarray(env.sys.actuator_biasprm)[:, 1].tolist(),
+                    "bias2": np.asarray(env.sys.actuator_biasprm)[:, 2].tolist(), "timestep": float(env.sys.opt.timestep),
+                    "action_buffer_shape": list(np.asarray(env.initial_action_buffer()).shape), "imu_buffer": np.asarray(env.initial_imu_buffer()).tolist()}
+
     # ---- domain_randomize (domain_randomization.py:8-112) and randomize_qpos ----------------------------------------------
     sysm = mjcf.load(REF_XML)
     sysm = sysm.replace(actuator_gainprm=sysm.actuator_gainprm.at[:, 0].set(5.0),

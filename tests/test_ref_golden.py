@@ -114,6 +114,23 @@ def test_reference_own_tests_passed_under_the_stand_ins():
     assert r["returncode"] == 0 and "passed" in r["summary"] and "failed" not in r["summary"], r
 
 
+def test_constructor_derives_what_the_reference_derives():
+    """ids, start pose, gain / bias overrides and time steps of PupperV3Env.__init__ (environment.py:165-244)."""
+    c = META["ctor"]
+    env = common.make_env()
+    np.testing.assert_allclose(env._init_q, np.asarray(c["init_q"], np.float32), rtol=0, atol=0)
+    assert env._torso_idx == c["torso_idx"] and list(env._feet_site_id) == c["feet_site_id"]
+    assert list(env._lower_leg_body_id) == c["lower_leg_body_id"] and list(env._upper_leg_geom_ids) == c["upper_leg_geom_ids"]
+    assert list(env._torso_geom_ids) == c["torso_geom_ids"]
+    assert abs(env.dt - c["dt"]) < 1e-12 and int(env._n_frames) == c["n_frames"] and env._nv == c["nv"]
+    np.testing.assert_array_equal(env.sys.actuator_gainprm[:, 0], np.asarray(c["kp"], np.float32))
+    np.testing.assert_array_equal(env.sys.actuator_biasprm[:, 1], np.asarray(c["bias1"], np.float32))
+    np.testing.assert_array_equal(env.sys.actuator_biasprm[:, 2], np.asarray(c["bias2"], np.float32))
+    assert abs(env.sys.timestep - c["timestep"]) < 1e-12
+    assert c["action_buffer_shape"] == [12, env.env_cfg.n_latency] and np.asarray(c["imu_buffer"]).shape == (6, env.env_cfg.n_imu_latency)
+    assert env.env_cfg.n_frames == c["n_frames"] and list(np.asarray(c["imu_buffer"])[5]) == [-1.0] * env.env_cfg.n_imu_latency
+
+
 def test_domain_randomize_matches_the_reference_leaf_for_leaf():
     g = np.load(os.path.join(G, "ref_domain_randomization.npz"))
     env = common.make_env()
