@@ -51,6 +51,10 @@ namespace pupper {
 #else
 #define PHASE_SYNC() ((void)0)
 #endif
+#ifndef PUPPER_SYNC_MASK
+#define PUPPER_SYNC_MASK 0x0aa  // which of the 9 phase barriers of forward() are compiled in (A/B on one box, 3 rounds: 0x0aa +0.7 % at 65,536 envs and +1.3 % at 4096 over all nine; 0x000 is -2..4 %)
+#endif
+#define PHASE_SYNC_AT(i) do { if ((PUPPER_SYNC_MASK >> (i)) & 1) PHASE_SYNC(); } while (0)
 constexpr int kBlock = PUPPER_BLOCK;   // threads per CTA
 constexpr int kEnvsPerBlock = kBlock / 4;
 constexpr int kMaxCon = 5;            // contact slots per env (max_contact_points <= 5)
@@ -1119,7 +1123,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   const int b0 = 2 + 3 * k;   // first body of this leg
   const float dt = m.timestep;
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(0);
   // ---- kinematics (A.2) ------------------------------------------------------------------------
   Q4 q1 = qnormalize(Q4{L.qb[3], L.qb[4], L.qb[5], L.qb[6]});
   L.qb[3] = q1.w; L.qb[4] = q1.x; L.qb[5] = q1.y; L.qb[6] = q1.z;
@@ -1195,7 +1199,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     C = mt < kMinVal ? xip_b : V3{pt.x / mt, pt.y / mt, pt.z / mt};
   }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(1);
   // ---- cinert, cdof (A.3) -------------------------------------------------------------------------
   Inertia ci[3], cib;
 #pragma unroll
@@ -1224,7 +1228,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int i = 0; i < 3; i++) bo[i] = cross(ba[i], ob);
   }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(2);
   // ---- velocities, RNE bias forces (A.7) -------------------------------------------------------------
   S6 cvb;  // base spatial velocity
   cvb.a = L.vb[3] * ba[0] + L.vb[4] * ba[1] + L.vb[5] * ba[2];
@@ -1336,7 +1340,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   for (int d = 0; d < 6; d++) fs_b[d] = -m.dof_damping[d] * L.vb[d] - bias_b[d];
   if (want_stale) { es.st_leg[k][12] = frc[0]; es.st_leg[k][13] = frc[1]; es.st_leg[k][14] = frc[2]; }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(3);
   // ---- collision (A.5): keep only contacts that can act (dist < 0), at most max_contact_points ------
   __syncwarp(qm);  // sphere centres visible to the quad
   int ncon = 0;
@@ -1478,7 +1482,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   const int ss_mask_w = plane_only ? 0 : (int)__reduce_or_sync(qm, (unsigned)ss_mask);  // slots holding a leg-leg contact somewhere in the warp
   const int nown_w = __reduce_max_sync(qm, own_count);  // most world-vs-leg contacts on one leg, over the warp
   if (want_stale && k == 0) { es.st_hits[0] = knee_hits; es.st_hits[1] = torso_hits; }
-  PHASE_SYNC();
+  PHASE_SYNC_AT(4);
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
   // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
   float *rowA = rows + threadIdx.x, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
@@ -1512,7 +1516,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     tree_solve(F, fs_b, fs_l, sb, sl, qm);
   }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(5);
   // ---- Newton solver, one iteration (A.8) ------------------------------------------------------------------
   // cost at the warm start and at qacc_smooth.  (M qacc_smooth is taken as qfrc_smooth.)
   float Maw_b[6], Maw_l[3];
@@ -1605,7 +1609,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     lJ[j] = use_w ? jaw_l[j] : jas_l[j];
   }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(6);
   // forces, J^T f, gradient; Hessian additions
   float gb[6], gl[3];
   // H is built in place in M's registers; the copy of M in shared memory serves the line search's M*search
@@ -1757,7 +1761,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     for (int i = 0; i < 3; i++) gb[3 + i] = Mab[3 + i] - fs_b[3 + i] - (dot(ba[i], Sb.a) + dot(bo[i], Sb.l));
   }
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(7);
   // Newton direction: search = -H^-1 grad
   float hb[6], hl[3];
   if (__any_sync(qm, dense_env)) {  // very rare: some env of this warp has two or more leg-leg contacts (H holds M + diagonal terms there)
@@ -1804,7 +1808,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
 #pragma unroll
   for (int j = 0; j < 3; j++) hl[j] = -hl[j];
 
-  PHASE_SYNC();
+  PHASE_SYNC_AT(8);
   // ---- line search along `search` (A.8.3) ---------------------------------------------------------------------
   float alpha;
   {
