@@ -316,21 +316,28 @@ def run_cuda(args):
         rand = functools.partial(dr.domain_randomize, rng=parallel.shard_keys(2, world * en, rank, world))
         tenv = wrappers.wrap(env_r, episode_length=1000, randomization_fn=rand)
         st = tenv.reset(torch.from_numpy(np.ascontiguousarray(parallel.shard_keys(0, world * en, rank, world)).view(np.int32)).to(dev))
-        col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env_r.observation_size, precision=1), st, T, use_cuda_graph=True)
-        for _ in range(5):
-            col.collect()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(10):
-            col.collect()
-        s1.record()
-        barrier()
-        roll_ms = max_over_ranks(s0.elapsed_time(s1))
+        pol_r = rollout.PolicyMLP.random(env_r.observation_size, precision=1)
+        roll = {}
+        for mode in ("graph", "one_launch"):
+            col = rollout.RolloutCollector(tenv, pol_r, st, T, use_cuda_graph=True, fused=mode == "one_launch")
+            for _ in range(5):
+                col.collect()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(10):
+                col.collect()
+            s1.record()
+            barrier()
+            roll[mode] = world * en * T * 10 / (max_over_ranks(s0.elapsed_time(s1)) * 1e-3)
         configs["configs[4] rollout collection"] = {
-            "value": world * en * T * 10 / (roll_ms * 1e-3), "unit": UNIT, "envs_per_gpu": en, "unroll": T,
+            "value": roll["graph"], "unit": UNIT, "envs_per_gpu": en, "unroll": T,
+            "one_launch_variant": roll["one_launch"],
             "note": "policy MLP 72-256-128-128-128-12 (stand-in for the JAX policy: TF32 on the tcgen05 kernel, XLA's default float32 "
-                    "matmul precision) + fused env step, one CUDA graph per unroll, max over ranks"}
+                    "matmul precision) + fused env step; per unroll ONE CUDA graph of 20 x (policy kernel that also files obs[t], env "
+                    "step that writes reward[t] / done[t] into the trajectory), max over ranks; one_launch_variant = pupper_rollout "
+                    "(the whole unroll as one kernel: policy phase + env step per CTA, steps chained on the device), kept opt-in "
+                    "because it is slower (instruction-fetch bound, DESIGN.md section 4)"}
 
     if rank != 0:
         if world > 1:

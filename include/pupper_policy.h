@@ -57,6 +57,32 @@ int pupper_policy_destroy(PupperPolicy *policy);
 /* action[n, out_dims[last]] = MLP(obs[n, in_dims[0]]); both device pointers, row-major, 16-byte aligned rows are NOT
  * required.  One kernel launch. */
 int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, float *action, pupper_stream_t stream);
+/* Same, and the observation rows the kernel reads are also written to obs_record[n, in_dims[0]] (device pointer, may be NULL,
+ * must not alias obs): the per-step rollout files obs[t] this way instead of with a separate copy. */
+int pupper_policy_forward_record(const PupperPolicy *policy, int n, const float *obs, float *action, float *obs_record,
+                                 pupper_stream_t stream);
+
+/* Rollout collection, ONE launch per unroll (BASELINE configs[4]).  What it replaces in the reference's
+ * training stack: Brax PPO's unroll (`brax.training.acting.generate_unroll` [3P]: a `lax.scan` of unroll_length x
+ * (policy forward, env.step) over the wrapped env -- the reference hands it PupperV3Env through `brax.envs.training.wrap`,
+ * pupperv3_mjx/environment.py:348 is the step it scans).  For t = 0 .. unroll_length - 1:
+ *     traj_obs[t]    = state->obs                        [n_envs][observation_history * 36]
+ *     traj_action[t] = policy(traj_obs[t])               [n_envs][12]   (deterministic head, as export.py:39-41 exports it)
+ *     state, traj_reward[t], traj_done[t] = pupper_step(state, traj_action[t])   (episode / auto-reset block included)
+ * All trajectory pointers are device memory, [unroll_length] slices back to back.  After the call `state` (and out->reward /
+ * done / metrics) are what unroll_length successive pupper_step calls with those actions would have left -- bit for bit,
+ * it is the same device code.  The policy's input width must be observation_history * 36, its output width 12, its layers
+ * at most 256 wide; debug taps of `out` must be NULL; unroll_length <= 65535.
+ * One kernel launch: a grid of (env groups of 32) x (steps); the CTA of (group, step) waits for the CTA of (group, step - 1)
+ * through a per-group counter in device memory (allocated by the first call for a batch size: make that call outside a
+ * stream capture; later calls only enqueue and are CUDA-graph capturable).  Groups never wait for each other.  Setting
+ * PUPPER_ROLLOUT_PER_STEP in the environment before the first call switches to one launch per step (diagnostics). */
+int pupper_rollout(const PupperModel *model, const PupperPolicy *policy, int n_envs, int unroll_length, const PupperDR *dr,
+                   PupperState *state, PupperStepOut *out, PupperEpisode *episode, float *traj_obs, float *traj_action,
+                   float *traj_reward, float *traj_done, pupper_stream_t stream);
+/* Number of waits of the chained launch that timed out so far (always 0 unless the device dispatched CTAs out of order;
+ * synchronises the device).  Negative: PUPPER_E* code. */
+int pupper_rollout_timeouts(const PupperModel *model);
 
 #ifdef __cplusplus
 }

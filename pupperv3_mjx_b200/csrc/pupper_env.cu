@@ -180,33 +180,45 @@ __device__ __forceinline__ uint2 get_obs(const BlockShared &sh, const KParams &p
 #else
 #define PUPPER_LB __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS)
 #endif
-template <bool RESET, bool DBG>
-__global__ void PUPPER_LB env_kernel(const KParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
-  {
+// Per-call pointers of one env step: what a single-step launch takes from KParams, and what the persistent rollout kernel
+// (pupper_rollout.cuh) moves from step to step of its unroll: there the three pointers are the [T][n][...] trajectory bases
+// and `t` selects the slice.
+struct StepIO {
+  const float *action;  // [n][12]
+  float *reward, *done; // [n]
+  int t;                // step of the unroll (0 for single-step launches)
+};
+
+// The whole reset / step of the CTA's 32 envs (CTA index `block`, thread index `tid`).  STAGED: the model constants, the per-env
+// DR leaves and the cleared contact slots are already in shared memory (the rollout kernel stages them itself, ahead of its
+// wait for the previous step), and io.t selects the trajectory slice.
+template <bool RESET, bool DBG, bool STAGED>
+__device__ __forceinline__ void env_body(const KParams &p, BlockShared &sh, const StepIO io, const int block, const int tid) {
+  if (!STAGED) {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.consts);
     uint4 *dst = reinterpret_cast<uint4 *>(static_cast<ConstBlock *>(&sh));
     constexpr int n16 = (int)(sizeof(ConstBlock) / 16);
 #pragma unroll
     for (int i0 = 0; i0 < n16; i0 += kBlock) {
-      const int i = i0 + threadIdx.x;
+      const int i = i0 + tid;
       if (i < n16) dst[i] = __ldg(src + i);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  const int lane = threadIdx.x & 31, k = threadIdx.x & 3;
-  const int el = threadIdx.x >> 2;
+  const int lane = tid & 31, k = tid & 3;
+  const int el = tid >> 2;
   // Every shuffle uses the full warp mask, so all 32 lanes stay convergent: quads past the end of the
   // batch recompute the last env (identical values) and their lanes write nothing different.
-  const bool valid = blockIdx.x * kEnvsPerBlock + el < p.n_envs;
-  const int e = min(blockIdx.x * kEnvsPerBlock + el, p.n_envs - 1);
+  const bool valid = block * kEnvsPerBlock + el < p.n_envs;
+  const int e = min(block * kEnvsPerBlock + el, p.n_envs - 1);
   const unsigned qm = 0xffffffffu;
   const int qbase = lane & 28;
   const PupperModelDesc &m = sh.m;
   const PupperEnvCfg &c = sh.c;
   EnvShared &es = sh.env[el];
   const int stride = p.st.stride;
+  // slice `t` of a trajectory array (single-step launches: t = 0, the arrays are the step's own)
+  auto at_step = [&](auto *base, int per_step) { return STAGED ? base + (size_t)io.t * per_step : base; };
   // external randoms: only the debug / parity instantiation looks at them (pupper_step routes calls that pass them there)
   const float *ext = (DBG && p.has_rand) ? p.rand.u + e : nullptr;
   const int ext_s = (DBG && p.has_rand) ? p.rand.stride : 0;
@@ -214,7 +226,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   // ---- stage the per-env DR leaves (or the nominal values) in shared memory --------------------------
   // Rolled loops on purpose (code size); the per-env leaves travel global -> shared as 4-byte async copies, so the
   // up-to-15 loads of a lane are all in flight at once without passing through registers.
-  {
+  if (!STAGED) {
     float *ef = reinterpret_cast<float *>(&es);  // mass[13] inertia[39] ipos[3] friction kp kd are contiguous
     if (p.has_dr) {
       const int ds = p.dr.stride;
@@ -236,13 +248,13 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   }
   // Contact slots are read (and multiplied by zero weights) by quads that have fewer contacts than the warp
   // maximum, so they must never hold non-finite garbage: clear them once per launch.
-  {
+  if (!STAGED) {
     float *cz = reinterpret_cast<float *>(es.con);
     for (int i = k; i < (int)(sizeof(es.con) / 4); i += 4) cz[i] = 0.f;
     if (k == 0) es.ncon = 0;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp(qm);
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncwarp(qm);
 
   LaneState L;
   StaleOut so;
@@ -271,7 +283,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     for (int j = 0; j < 3; j++) { L.ql[j] = c.init_q[7 + 3 * k + j]; L.vl[j] = 0.f; L.wl[j] = 0.f; L.ctrl[j] = 0.f; }
 #pragma unroll
     for (int d = 0; d < 6; d++) { L.vb[d] = 0.f; L.wb[d] = 0.f; }
-    forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, true, &dbg);
+    forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, true, &dbg, tid);
     __syncwarp(qm);
     so = load_stale(es, k);  // pipeline_init = make_data + forward
 #pragma unroll
@@ -298,7 +310,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     if (k == 0) {
       if (valid) p.st.last_contact[e] = 0u; if (valid) p.st.step[e] = 0;
       if (valid) p.st.kick[e] = 0.f; if (valid) p.st.kick[stride + e] = 0.f;
-      if (valid) p.out.reward[e] = 0.f; if (valid) p.out.done[e] = 0.f;
+      if (valid) io.reward[e] = 0.f; if (valid) io.done[e] = 0.f;
     }
     for (int i = k; i < PUPPER_NMETRIC; i += 4) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + i] = 0.f;
   } else {
@@ -366,7 +378,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
 #pragma unroll
     for (int j = 0; j < 3; j++) {
       const int u_ = 3 * k + j;
-      act[j] = p.action[(size_t)e * PUPPER_NU + u_];
+      act[j] = at_step(io.action, p.n_envs * PUPPER_NU)[(size_t)e * PUPPER_NU + u_];
       float lag = push_front_pick(p.st.action_buffer + (size_t)(u_ * La) * stride + e, stride, La, act[j], aidx, false, 0.f, valid);
       float t = c.default_pose[u_] + lag * c.action_scale;
       L.ctrl[j] = fminf(fmaxf(t, c.joint_lower[u_]), c.joint_upper[u_]);
@@ -377,7 +389,7 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
     // S5 physics: n_frames x (forward ; semi-implicit Euler)
     const float dt = m.timestep;
     for (int f = 0; f < c.n_frames; f++) {
-      forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, f == c.n_frames - 1, &dbg);
+      forward<DBG>(sh, es, sh.rows, L, k, qm, qbase, ab, al, f == c.n_frames - 1, &dbg, tid);
 #pragma unroll
       for (int d = 0; d < 6; d++) { L.wb[d] = ab[d]; L.vb[d] = fmaf(ab[d], dt, L.vb[d]); }
 #pragma unroll
@@ -696,9 +708,16 @@ __global__ void PUPPER_LB env_kernel(const KParams p) {
   }
 
   // ---- S12 outputs ------------------------------------------------------------------------------------------------------
-  if (k == 0) { if (valid) p.out.reward[e] = reward; if (valid) p.out.done[e] = fdone; if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
+  if (k == 0) { if (valid) at_step(io.reward, p.n_envs)[e] = reward; if (valid) at_step(io.done, p.n_envs)[e] = fdone; if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
 #pragma unroll
   for (int q = 0; q < PUPPER_NREWARD; q++) if ((q & 3) == k) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + 1 + q] = rw[q];
+}
+
+template <bool RESET, bool DBG>
+__global__ void PUPPER_LB env_kernel(const KParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BlockShared &sh = *reinterpret_cast<BlockShared *>(smem_raw);
+  env_body<RESET, DBG, false>(p, sh, StepIO{p.action, p.out.reward, p.out.done, 0}, (int)blockIdx.x, (int)threadIdx.x);
 }
 
 }  // namespace pupper
@@ -726,6 +745,10 @@ struct PupperModel {
   PupperModelDesc h_desc;
   PupperEnvCfg h_cfg;
   int last_launches;
+  bool rollout_ready;  // shared-memory attribute of the rollout kernels set on this model's device (first pupper_rollout call)
+  bool rollout_chain;  // chained grid (one launch per unroll) or one launch per step
+  int *group_step;     // device: per-env-group step counters of the chained launch
+  int group_step_len;
 };
 
 static thread_local char g_cuda_err[256] = "";
@@ -800,6 +823,10 @@ int pupper_model_create(const PupperModelDesc *desc, const PupperEnvCfg *cfg, in
   m->h_desc = *desc;
   m->h_cfg = *cfg;
   m->last_launches = 0;
+  m->rollout_ready = false;
+  m->rollout_chain = true;
+  m->group_step = nullptr;
+  m->group_step_len = 0;
   // constants that do not depend on the state: friction-loss rows have pos = 0, so their impedance is fixed
   pupper::DerivedConsts dc;
   memset(&dc, 0, sizeof(dc));
@@ -849,6 +876,7 @@ int pupper_model_destroy(PupperModel *m) {
   if (!m) return PUPPER_EINVAL;
   cudaSetDevice(m->device);
   cudaFree(m->d_consts);
+  if (m->group_step) cudaFree(m->group_step);
   delete m;
   return PUPPER_OK;
 }
@@ -950,3 +978,5 @@ int pupper_state_rows(const PupperEnvCfg *cfg, int32_t *rows_out) {
 
 // policy-MLP forward pass (include/pupper_policy.h): same library, same error helpers
 #include "pupper_policy.cuh"
+// persistent rollout kernel: policy phase + env phase, T steps per launch (include/pupper_policy.h pupper_rollout)
+#include "pupper_rollout.cuh"

@@ -1118,7 +1118,7 @@ __device__ __noinline__ void woodbury_direction(const EnvShared &es, WoodburyIO 
 // ---------------------------------------------------------------------------------------------------
 template <bool DBG>
 __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, float *rows, LaneState &L, int k, unsigned qm, int qbase,
-                                     float ab[6], float al[3], bool want_stale, DbgOut *dbg) {
+                                     float ab[6], float al[3], bool want_stale, DbgOut *dbg, const int tid) {
   const PupperModelDesc &m = sh.m;
   const int b0 = 2 + 3 * k;   // first body of this leg
   const float dt = m.timestep;
@@ -1485,8 +1485,8 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   PHASE_SYNC_AT(4);
   // ---- constraint rows handled by this lane (A.6): 3 friction-loss, 3 limits, one pyramid edge per contact
   // (contact-edge row scalars live in shared memory: row[buffer][contact][thread])
-  float *rowA = rows + threadIdx.x, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
-  float *rowQ = rows + (threadIdx.x & ~3);  // the same buffers seen from lane 0 of the quad: edge e of contact c at rowQ[c*kBlock + e]
+  float *rowA = rows + tid, *rowB = rowA + kMaxCon * kBlock, *rowC = rowB + kMaxCon * kBlock;
+  float *rowQ = rows + (tid & ~3);  // the same buffers seen from lane 0 of the quad: edge e of contact c at rowQ[c*kBlock + e]
   const float esgn = (k & 1) ? -1.f : 1.f;  // pyramid edge of this lane: Jn + esgn*mu*Jt[k>>1]
   const bool et2 = (k >> 1) != 0;
   float fl[3], rff[3], fD[3], fA[3];   // friction-loss rows: loss, R*loss, D, aref
@@ -1614,7 +1614,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   float gb[6], gl[3];
   // H is built in place in M's registers; the copy of M in shared memory serves the line search's M*search
   {
-    float *msm = const_cast<float *>(sh.mat) + threadIdx.x;
+    float *msm = const_cast<float *>(sh.mat) + tid;
 #pragma unroll
     for (int i = 0; i < 21; i++) msm[i * kBlock] = M.B[i];
 #pragma unroll
@@ -1813,7 +1813,7 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
   float alpha;
   {
     float mvb[6], mvl[3];
-    tree_matvec_smem(sh.mat + threadIdx.x, hb, hl, mvb, mvl, qm);
+    tree_matvec_smem(sh.mat + tid, hb, hl, mvb, mvl, qm);
     {
       float v1b[1][6], v1l[1][3];
 #pragma unroll
@@ -1846,9 +1846,9 @@ __device__ __forceinline__ void forward(const BlockShared &sh, EnvShared &es, fl
     // Quadratic models of this lane's rows, built once per line search and kept in lane-private shared memory (the
     // stage loop then needs two 16-byte loads per friction row, one 16-byte + one 4-byte load per contact-edge row).
     // The cost model at alpha = 0 (MJX's p0) falls out of the same pass: same sums, same order as eval3 below.
-    float4 *lsf = const_cast<float4 *>(sh.lsf) + threadIdx.x;
-    float4 *lsq = const_cast<float4 *>(sh.lsq) + threadIdx.x;
-    float *lsc = const_cast<float *>(sh.lsc) + threadIdx.x;
+    float4 *lsf = const_cast<float4 *>(sh.lsf) + tid;
+    float4 *lsq = const_cast<float4 *>(sh.lsq) + tid;
+    float *lsc = const_cast<float *>(sh.lsc) + tid;
     float fb0 = 0.f, fb1 = 0.f, fb2 = 0.f;  // friction rows: quadratic-zone coefficients, common to all step sizes
     float fc[3][4];                         // friction rows: linear-zone corrections (kept for the alpha = 0 pass only)
 #pragma unroll

@@ -44,6 +44,7 @@ struct PolicyParams {
   int n;
   const float *obs;
   float *action;
+  float *obs_record;  // optional [n][in_dim]: copy of the observation rows read (the rollout's trajectory slice)
 };
 
 // TF32 head of a float by truncation (the tensor core ignores the low 13 mantissa bits of its operands anyway, so the
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(32 * kPolWarps * NSPLIT) policy_kernel(const P
       for (int u = 0; u < 8; u++) {
         const int i = base + u * 32 * NSPLIT + gl, r = i / kp0, c = i - r * kp0;
         if (i < total) rows[r * p.stride + c] = v[u];
+        if (p.obs_record && i < total && row0 + r < p.n && c < p.in_dim) p.obs_record[(size_t)(row0 + r) * p.in_dim + c] = v[u];
       }
     }
   }
@@ -401,14 +403,18 @@ int pupper_policy_tc_trace(long long *host256) {
 #endif
 
 int pupper_policy_forward(const PupperPolicy *policy, int n, const float *obs, float *action, pupper_stream_t stream) {
-  if (!policy || !obs || !action || n <= 0) return PUPPER_EINVAL;
+  return pupper_policy_forward_record(policy, n, obs, action, nullptr, stream);
+}
+
+int pupper_policy_forward_record(const PupperPolicy *policy, int n, const float *obs, float *action, float *obs_record, pupper_stream_t stream) {
+  if (!policy || !obs || !action || n <= 0 || obs_record == obs) return PUPPER_EINVAL;
   pupper::PolicyParams p = policy->params;
-  p.n = n; p.obs = obs; p.action = action;
+  p.n = n; p.obs = obs; p.action = action; p.obs_record = obs_record;
   const int grid = (n + pupper::kPolRows - 1) / pupper::kPolRows;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (policy->use_tc) {
     pupper::TcParams t = policy->tc;
-    t.n = n; t.obs = obs; t.action = action;
+    t.n = n; t.obs = obs; t.action = action; t.obs_record = obs_record;
     const int grid = (n + pupper::kTcRows - 1) / pupper::kTcRows;
     if (policy->tc_v2) pupper::policy_tc2_kernel<<<grid, pupper::kTc2Threads, pupper::kTcSmemBytes, s>>>(t);
     else pupper::policy_tc_kernel<<<grid, pupper::kTcThreads, pupper::kTcSmemBytes, s>>>(t);

@@ -55,6 +55,7 @@ struct TcParams {
   int n_chunks, n_layers, in_dim, n;
   const float *obs;
   float *action;
+  float *obs_record;  // optional [n][in_dim]: the staged observation rows are also written here (the rollout's trajectory slice)
 };
 
 #ifdef PUPPER_TC_TRACE  // timeline of CTA 0 (clock64 stamps; slot layout in tools/tc_trace.py), exported through pupper_policy_tc_trace
@@ -213,6 +214,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) policy_tc_kernel(const __grid_c
         const int id = base + u * kTcThreads + tid;
         const int r = id / kq, c4 = id - r * kq;
         if (id < kTcRows * kq) *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v[u];
+        if (p.obs_record && id < kTcRows * kq && row0 + r < p.n) {
+          float *o = p.obs_record + (size_t)(row0 + r) * p.in_dim + 4 * c4;
+          if (vec && 4 * c4 + 3 < p.in_dim && (reinterpret_cast<uintptr_t>(p.obs_record) & 15) == 0) *reinterpret_cast<float4 *>(o) = v[u];
+          else {
+            if (4 * c4 < p.in_dim) o[0] = v[u].x;
+            if (4 * c4 + 1 < p.in_dim) o[1] = v[u].y;
+            if (4 * c4 + 2 < p.in_dim) o[2] = v[u].z;
+            if (4 * c4 + 3 < p.in_dim) o[3] = v[u].w;
+          }
+        }
       }
     }
   }
@@ -409,6 +420,16 @@ __global__ void __launch_bounds__(kTc2Threads, 1) policy_tc2_kernel(const __grid
           const int id = base + u * kTcThreads + tid;
           const int r = id / kq, c4 = id - r * kq;
           if (id < kTcRows * kq) *reinterpret_cast<float4 *>(smA + (r & 7) * 16 + c4 * 128 + (r >> 3) * kTcSboA) = v[u];
+          if (p.obs_record && id < kTcRows * kq && row0 + r < p.n) {
+            float *o = p.obs_record + (size_t)(row0 + r) * p.in_dim + 4 * c4;
+            if (vec && 4 * c4 + 3 < p.in_dim && (reinterpret_cast<uintptr_t>(p.obs_record) & 15) == 0) *reinterpret_cast<float4 *>(o) = v[u];
+            else {
+              if (4 * c4 < p.in_dim) o[0] = v[u].x;
+              if (4 * c4 + 1 < p.in_dim) o[1] = v[u].y;
+              if (4 * c4 + 2 < p.in_dim) o[2] = v[u].z;
+              if (4 * c4 + 3 < p.in_dim) o[3] = v[u].w;
+            }
+          }
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -8,6 +8,8 @@ pass; measured on B200 at 8192 rows: 48 us per call with float32-level accuracy 
 (``csrc/pupper_policy_tc.cuh``), against 83 us for the graph-replayed torch/cuBLAS layers) or by torch/cuBLAS
 (``impl="torch"``, the float32 checker the tests compare against).  One unroll = ``unroll_length`` x (policy forward + fused env step); nothing synchronises
 with the host, so the whole unroll can be captured in a CUDA graph.
+
+``RolloutCollector(fused=True)`` runs the whole unroll as ONE kernel launch (``csrc/pupper_rollout.cuh``); see the class.
 """
 
 from __future__ import annotations
@@ -53,9 +55,13 @@ class PolicyMLP(torch.nn.Module):
         return cls(export.policy_from_dict(policy_dict), device, **kw)
 
     @torch.no_grad()
-    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None, record: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``record``: buffer shaped like ``obs`` that receives a copy of the rows read (the CUDA policy writes it from the
+        kernel that stages the rows anyway; the torch policy copies)."""
         if self._kernel is not None:
-            return self._kernel.forward(obs, out)
+            return self._kernel.forward(obs, out, record)
+        if record is not None:
+            record.copy_(obs)
         x = obs
         for W, b, act in zip(self.weights, self.biases, self.acts):
             x = act(torch.addmm(b, x, W))
@@ -66,23 +72,32 @@ class PolicyMLP(torch.nn.Module):
 
 
 class RolloutCollector:
-    """Preallocated [T, B, ...] buffers + optional CUDA-graph capture of one unroll."""
+    """Preallocated [T, B, ...] trajectory buffers and one of two ways to fill them:
 
-    def __init__(self, tenv, policy: PolicyMLP, state: State, unroll_length: int, use_cuda_graph: bool = True):
+    * per step (default): ``unroll_length`` x (policy launch, env-step launch), captured in ONE CUDA graph.  Nothing else is
+      launched: the policy kernel files ``obs[t]`` while it stages the rows it reads (``pupper_policy_forward_record``), and
+      the env step writes ``reward[t]`` / ``done[t]`` straight into the trajectory (the C ABI's output pointers are
+      caller-owned);
+    * ``fused=True``: the whole unroll as ONE kernel launch (``pupper_rollout``, ``csrc/pupper_rollout.cuh``: a grid of
+      (env groups) x (steps), the policy phase and the env step of a group and step in one CTA, steps of a group chained
+      through a device-side counter).  Bit-identical to the per-step path for the same actions; measured SLOWER on B200
+      (8192 envs: 160 us per step against 109 us): the step kernel is bound by instruction fetch, and a CTA that alternates
+      between the policy's code and the env step's 140 KB runs both cold, where the separate kernels run them hot.  Kept for
+      what it shows and as the one-launch entry point of the C ABI; not the default."""
+
+    def __init__(self, tenv, policy: PolicyMLP, state: State, unroll_length: int, use_cuda_graph: bool = True,
+                 fused: bool = False):
         self.tenv, self.policy, self.state, self.T = tenv, policy, state, int(unroll_length)
         B, dev = state.obs.shape[0], state.obs.device
-        rt = state.pipeline_state.runtime
-        # The runtime keeps obs | reward | done of the last step back to back (packed_outputs), so ONE copy per step files
-        # all three: slot 0 holds the state the unroll starts from, slot t + 1 what step t produced.  obs[t] (the policy
-        # input of step t) is slot t, reward[t] / done[t] are slot t + 1.
-        self._slots = torch.empty((self.T + 1, rt.packed_outputs().numel()), device=dev)
-        w, rows = state.obs.shape[1], rt.n_envs + rt.guard_rows  # layout of packed_outputs: obs[rows, w] | reward[rows] | done[rows]
-        self.obs = self._slots[: self.T, : rows * w].unflatten(1, (rows, w))[:, :B]
-        self.reward = self._slots[1:, rows * w: rows * w + B]
-        self.done = self._slots[1:, rows * (w + 1): rows * (w + 1) + B]
+        self.fused = bool(fused)
+        if self.fused and policy._kernel is None:
+            raise ValueError("fused=True needs PolicyMLP(impl='cuda')")
+        self.obs = torch.empty((self.T, B, state.obs.shape[1]), device=dev)
         self.action = torch.empty((self.T, B, 12), device=dev)
+        self.reward = torch.empty((self.T, B), device=dev)
+        self.done = torch.empty((self.T, B), device=dev)
         self._graph: Optional[torch.cuda.CUDAGraph] = None
-        if use_cuda_graph:
+        if use_cuda_graph and not self.fused:
             self._unroll()  # warm-up (allocator, cuBLAS handles) outside the capture
             torch.cuda.synchronize()
             s = torch.cuda.Stream()
@@ -96,14 +111,14 @@ class RolloutCollector:
 
     def _unroll(self):
         rt = self.state.pipeline_state.runtime
-        self._slots[0].copy_(rt.packed_outputs())
         for t in range(self.T):
-            self.policy(rt.obs, self.action[t])  # written in place (the CUDA policy needs no temporary)
-            rt.step(self.action[t])
-            self._slots[t + 1].copy_(rt.packed_outputs())
+            self.policy(rt.obs, self.action[t], self.obs[t])  # action written in place, obs[t] filed by the same kernel
+            rt.step(self.action[t], reward_out=self.reward[t], done_out=self.done[t])
 
     def collect(self) -> Dict[str, torch.Tensor]:
-        if self._graph is not None:
+        if self.fused:
+            self.state.pipeline_state.runtime.rollout(self.policy._kernel, self.obs, self.action, self.reward, self.done)
+        elif self._graph is not None:
             self._graph.replay()
         else:
             self._unroll()

@@ -48,6 +48,10 @@ def load_library() -> C.CDLL:
         lib.pupper_policy_create.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.pupper_policy_destroy.argtypes = [C.c_void_p]
         lib.pupper_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_policy_forward_record.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_rollout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.pupper_rollout_timeouts.argtypes = [C.c_void_p]
         for i, s in enumerate((abi.PupperModelDesc, abi.PupperEnvCfg, abi.PupperState, abi.PupperDR, abi.PupperStepOut,
                                abi.PupperEpisode, abi.PupperRand)):
             if lib.pupper_sizeof(i) != C.sizeof(s):
@@ -189,6 +193,7 @@ class EnvRuntime:
         self.done, self.metrics = self._done_full[: self.n_envs], self._metrics_full[: self.n_envs]
         self.state.obs = self.obs.data_ptr()
         self.out = abi.PupperStepOut()
+        self._out_variants = {}  # (reward ptr, done ptr) -> PupperStepOut with those two outputs redirected (step(reward_out=, done_out=))
         self.out.reward, self.out.done, self.out.metrics = self.reward.data_ptr(), self.done.data_ptr(), self.metrics.data_ptr()
         self.dbg: Dict[str, torch.Tensor] = {}
         if debug:
@@ -289,19 +294,62 @@ class EnvRuntime:
         _check(self.lib, rc, "pupper_reset")
         self.launches += self.lib.pupper_last_launch_count(self._model)
 
-    def step(self, action: torch.Tensor, ext_rand: Optional[torch.Tensor] = None, with_episode: bool = True):
+    def step(self, action: torch.Tensor, ext_rand: Optional[torch.Tensor] = None, with_episode: bool = True,
+             reward_out: Optional[torch.Tensor] = None, done_out: Optional[torch.Tensor] = None):
         """One env step.  ``with_episode=False`` runs the bare env step even when the fused Episode / AutoReset block is
-        allocated (the inner steps of an ``action_repeat`` > 1 wrapper step)."""
+        allocated (the inner steps of an ``action_repeat`` > 1 wrapper step).  ``reward_out`` / ``done_out`` (contiguous
+        float32 ``[n_envs]`` on the env's device, both or neither) receive the step's reward and done flags INSTEAD of the
+        runtime's own buffers -- the C ABI's output pointers are caller-owned, so a rollout files them in its trajectory
+        slices without a copy."""
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
                 or action.numel() != self.n_envs * abi.NU:
             raise PupperError("action must be a contiguous float32 CUDA tensor of shape [n_envs, 12] on the env's device")
+        out = self.out
+        if (reward_out is None) != (done_out is None):
+            raise PupperError("reward_out and done_out come as a pair")
+        if reward_out is not None:
+            for t in (reward_out, done_out):
+                if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != self.n_envs:
+                    raise PupperError("reward_out / done_out must be contiguous float32 CUDA tensors of n_envs elements on the env's device")
+            key = (reward_out.data_ptr(), done_out.data_ptr())
+            out = self._out_variants.get(key)
+            if out is None:
+                out = abi.PupperStepOut()
+                C.memmove(C.byref(out), C.byref(self.out), C.sizeof(out))
+                out.reward, out.done = key
+                if len(self._out_variants) > 4096:
+                    self._out_variants.clear()
+                self._out_variants[key] = out
         rand = self._rand_struct(ext_rand)
         with torch.cuda.device(self.device):
             rc = self.lib.pupper_step(self._model, self.n_envs, C.byref(self._dr_struct) if self._dr_struct else None,
                                       C.byref(self.state), action.data_ptr(), C.byref(rand) if rand is not None else None,
-                                      C.byref(self.out), C.byref(self.episode) if (self.episode and with_episode) else None, self._stream())
+                                      C.byref(out), C.byref(self.episode) if (self.episode and with_episode) else None, self._stream())
         _check(self.lib, rc, "pupper_step")
         self.launches += 1
+
+    def rollout(self, policy: "PolicyRuntime", obs: torch.Tensor, action: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+        """One unroll in ONE kernel launch (include/pupper_policy.h ``pupper_rollout``): for t in range(T), ``obs[t]`` = the
+        current observation, ``action[t] = policy(obs[t])``, env step, ``reward[t]`` / ``done[t]``.  Trajectory tensors are
+        contiguous float32 on the env's device: obs [T, n, H*36], action [T, n, 12], reward / done [T, n]."""
+        T, w = obs.shape[0], self.cfg.observation_history * abi.OBS_DIM
+        want = {"obs": (obs, (T, self.n_envs, w)), "action": (action, (T, self.n_envs, abi.NU)), "reward": (reward, (T, self.n_envs)),
+                "done": (done, (T, self.n_envs))}
+        for name, (t, shape) in want.items():
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+                raise PupperError(f"{name} must be a contiguous float32 CUDA tensor of shape {list(shape)} on the env's device")
+        if not isinstance(policy, PolicyRuntime) or policy.device != self.device:
+            raise PupperError("rollout needs a PolicyRuntime on the env's device")
+        with torch.cuda.device(self.device):
+            rc = self.lib.pupper_rollout(self._model, policy._handle, self.n_envs, T, C.byref(self._dr_struct) if self._dr_struct else None,
+                                         C.byref(self.state), C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                         obs.data_ptr(), action.data_ptr(), reward.data_ptr(), done.data_ptr(), self._stream())
+        _check(self.lib, rc, "pupper_rollout")
+        self.launches += self.lib.pupper_last_launch_count(self._model)
+
+    def rollout_timeouts(self) -> int:
+        """Waits of the chained rollout launch that timed out (0 in a healthy run; synchronises the device)."""
+        return int(self.lib.pupper_rollout_timeouts(self._model))
 
     # ---- host-buffer path: action in pinned host memory -> step -> obs | reward | done in pinned host memory ----------
     def _chunk_structs(self, chunks: int):
@@ -518,7 +566,8 @@ class PolicyRuntime:
         except Exception:
             pass
 
-    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None, record: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``record`` (same shape as ``obs``, another buffer): the kernel also writes the rows it reads there."""
         if obs.device != self.device or obs.dtype != torch.float32 or not obs.is_contiguous() or obs.dim() != 2 \
                 or obs.shape[1] != self.in_dim:
             raise PupperError(f"obs must be a contiguous float32 CUDA tensor of shape [n, {self.in_dim}] on the policy's device")
@@ -527,9 +576,13 @@ class PolicyRuntime:
             out = torch.empty((n, self.out_dim), dtype=torch.float32, device=self.device)
         elif out.shape != (n, self.out_dim) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.device:
             raise PupperError(f"out must be a contiguous float32 CUDA tensor of shape [{n}, {self.out_dim}]")
+        if record is not None and (record.shape != obs.shape or record.dtype != torch.float32 or not record.is_contiguous()
+                                   or record.device != self.device or record.data_ptr() == obs.data_ptr()):
+            raise PupperError("record must be a contiguous float32 CUDA tensor shaped like obs, in another buffer")
         with torch.cuda.device(self.device):
-            rc = self.lib.pupper_policy_forward(self._handle, n, obs.data_ptr(), out.data_ptr(),
-                                                torch.cuda.current_stream(self.device).cuda_stream)
+            rc = self.lib.pupper_policy_forward_record(self._handle, n, obs.data_ptr(), out.data_ptr(),
+                                                       record.data_ptr() if record is not None else None,
+                                                       torch.cuda.current_stream(self.device).cuda_stream)
         _check(self.lib, rc, "pupper_policy_forward")
         self.launches += 1
         return out

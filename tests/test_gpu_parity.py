@@ -567,7 +567,7 @@ def test_rollout_collector_graph_matches_eager():
         tenv = wrappers.wrap(env, episode_length=1000)
         st = tenv.reset(keys)
         pol = rollout.PolicyMLP.random(env.observation_size, seed=3)
-        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=use_graph)
+        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=use_graph, fused=False)
         if use_graph:  # construction ran one warm-up unroll; bring the eager twin to the same point
             pass
         r = col.collect()
@@ -578,7 +578,7 @@ def test_rollout_collector_graph_matches_eager():
     env = common.make_env()
     tenv = wrappers.wrap(env, episode_length=1000)
     st = tenv.reset(keys)
-    col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env.observation_size, seed=3), st, T, use_cuda_graph=False)
+    col = rollout.RolloutCollector(tenv, rollout.PolicyMLP.random(env.observation_size, seed=3), st, T, use_cuda_graph=False, fused=False)
     col.collect()
     r2 = col.collect()
     torch.cuda.synchronize()
@@ -741,7 +741,7 @@ def test_rollout_with_cuda_policy_matches_torch_policy():
         tenv = wrappers.wrap(env, episode_length=1000)
         st = tenv.reset(keys)
         pol = rollout.PolicyMLP.random(env.observation_size, impl=impl)
-        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=False)
+        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=False, fused=False)
         outs[impl] = {k: v.clone() for k, v in col.collect().items()}
     a, b = outs["torch"], outs["cuda"]
     assert torch.isfinite(b["obs"]).all() and torch.isfinite(b["action"]).all()
@@ -752,7 +752,7 @@ def test_rollout_with_cuda_policy_matches_torch_policy():
     tenv = wrappers.wrap(env, episode_length=1000)
     st = tenv.reset(keys)
     pol = rollout.PolicyMLP.random(env.observation_size, impl="cuda")
-    col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=True)
+    col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=True, fused=False)
     r1 = {k: v.clone() for k, v in col.collect().items()}
     assert torch.isfinite(r1["obs"]).all() and float(r1["action"].abs().max()) <= 1.0
     # the TF32 policy runs on the tcgen05 kernel (tensor memory, bulk async copies): eager and graph-replayed unrolls from
@@ -763,12 +763,68 @@ def test_rollout_with_cuda_policy_matches_torch_policy():
         tenv = wrappers.wrap(env, episode_length=1000)
         st = tenv.reset(keys)
         pol = rollout.PolicyMLP.random(env.observation_size, impl="cuda", precision=1)
-        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=use_graph)
+        col = rollout.RolloutCollector(tenv, pol, st, T, use_cuda_graph=use_graph, fused=False)
         if not use_graph:
             col.collect()  # the graph twin ran one warm-up unroll at construction
         res.append({k: v.clone() for k, v in col.collect().items()})
     for k in ("obs", "action", "reward", "done"):
         assert torch.equal(res[0][k], res[1][k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [3, 1])
+def test_one_launch_rollout_equals_step_by_step(precision):
+    """pupper_rollout (ONE launch per unroll: policy phase + env phase inside every CTA, csrc/pupper_rollout.cuh) against the
+    single-step entry points on a twin env: with the recorded actions the twin's pupper_step sequence reproduces every
+    observation, reward, done flag and the final state BIT FOR BIT (it is the same device code), and the recorded actions are
+    what the stand-alone policy kernel computes from the recorded observations (float32 level at 3xTF32, TF32 rounding at
+    TF32 -- the summation order of the two kernels differs).  Ragged batch (not a multiple of the 32 envs of a CTA), full
+    domain randomisation, the fused Episode / AutoReset block with short episodes so that auto-resets happen in the unroll."""
+    from pupperv3_mjx_b200 import rollout, wrappers
+    n, T = 200, 12
+    keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
+
+    def make():
+        import functools
+        env = common.make_env()
+        rand = functools.partial(dr.domain_randomize, rng=prng.split(prng.PRNGKey(2), n))
+        tenv = wrappers.wrap(env, episode_length=7, randomization_fn=rand)
+        return env, tenv, tenv.reset(keys)
+
+    env_a, tenv_a, st_a = make()
+    env_b, tenv_b, st_b = make()
+    pol = rollout.PolicyMLP.random(env_a.observation_size, impl="cuda", precision=precision, seed=5)
+    col = rollout.RolloutCollector(tenv_a, pol, st_a, T, fused=True)
+    assert col.fused
+    rt_a, rt_b = st_a.pipeline_state.runtime, st_b.pipeline_state.runtime
+    l0 = rt_a.launches
+    r = col.collect()
+    torch.cuda.synchronize()
+    assert rt_a.launches - l0 == 1, "one kernel launch per unroll"
+    assert rt_a.rollout_timeouts() == 0
+    assert torch.isfinite(r["obs"]).all() and torch.isfinite(r["reward"]).all() and float(r["action"].abs().max()) <= 1.0
+    assert float(r["done"].sum()) > 0, "episode_length 7 < T: some envs must have been auto-reset inside the unroll"
+    tol = 2e-5 if precision == 3 else 2e-2
+    for t in range(T):
+        assert torch.equal(rt_b.obs[:n], r["obs"][t]), f"obs at step {t}"
+        a_ref = pol(r["obs"][t].contiguous())
+        np.testing.assert_allclose(r["action"][t].cpu().numpy(), a_ref.cpu().numpy(), atol=tol, err_msg=f"action at step {t}")
+        rt_b.step(r["action"][t].contiguous())
+        rew, done = rt_b.split_packed(rt_b.packed_outputs())[1:]
+        assert torch.equal(rew[:n], r["reward"][t]), f"reward at step {t}"
+        assert torch.equal(done[:n], r["done"][t]), f"done at step {t}"
+    torch.cuda.synchronize()
+    for name in ("qpos", "qvel", "qacc_warmstart", "rng", "action_buffer", "imu_buffer", "last_act", "command", "step"):
+        assert torch.equal(rt_a.field(name), rt_b.field(name)), name
+    assert torch.equal(rt_a.obs[:n], rt_b.obs[:n])
+    for name in ("sum_reward", "length", "steps"):
+        assert torch.equal(rt_a.episode_field(name), rt_b.episode_field(name)), name
+    # the completed-episode accumulator is summed with atomics: same addends, another order
+    np.testing.assert_allclose(rt_a.episode_field("totals").cpu().numpy(), rt_b.episode_field("totals").cpu().numpy(), rtol=1e-5, atol=1e-3)
+    # a second unroll continues from where the first one stopped
+    r2 = {k: v.clone() for k, v in col.collect().items()}
+    torch.cuda.synchronize()
+    assert torch.equal(r2["obs"][0], rt_b.obs[:n])
 
 
 @pytest.mark.gpu

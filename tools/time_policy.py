@@ -39,6 +39,6 @@ def env_T():
     for _ in range(T): rt.step(act)
 print(f"n={n}: env step {timeit(env_T) / T * 1e3:.1f} us/step")
 for name, pc in (("torch policy", pol), ("fused policy 3xTF32", pol_c3), ("fused policy TF32", pol_c1)):
-    col = rollout.RolloutCollector(tenv, pc, st, T, use_cuda_graph=True)
+    col = rollout.RolloutCollector(tenv, pc, st, T, use_cuda_graph=True, fused=False)
     ms = timeit(col.collect, 10)
     print(f"n={n}: collector unroll, {name}: {ms / T * 1e3:.1f} us/step -> {n * T / (ms * 1e-3):.4g} env-steps/s")
