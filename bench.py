@@ -312,11 +312,11 @@ def run_cuda(args):
         import functools
         from pupperv3_mjx_b200 import rollout, wrappers
         en, T = 8192, 20
-        env_r = common.make_env()
+        env_r = common.make_env(device=local)
         rand = functools.partial(dr.domain_randomize, rng=parallel.shard_keys(2, world * en, rank, world))
         tenv = wrappers.wrap(env_r, episode_length=1000, randomization_fn=rand)
         st = tenv.reset(torch.from_numpy(np.ascontiguousarray(parallel.shard_keys(0, world * en, rank, world)).view(np.int32)).to(dev))
-        pol_r = rollout.PolicyMLP.random(env_r.observation_size, precision=1)
+        pol_r = rollout.PolicyMLP.random(env_r.observation_size, precision=1, device=dev)
         roll = {}
         for mode in ("graph", "one_launch"):
             col = rollout.RolloutCollector(tenv, pol_r, st, T, use_cuda_graph=True, fused=mode == "one_launch")

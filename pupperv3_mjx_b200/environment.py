@@ -106,7 +106,7 @@ class PupperV3Env:
         use_imu: bool = True,
         # --- extensions (not in the reference ctor) --------------------------------------------
         frictionloss_rows: bool = True,
-        device: int = 0,
+        device: Optional[int] = None,
     ):
         model = mjcf.compile_model(path, frictionloss_rows=frictionloss_rows)
         self._model = model
@@ -140,7 +140,7 @@ class PupperV3Env:
         self.observation_dim = 36
         self._latency_distribution = np.asarray(latency_distribution, dtype=np.float32)
         self._imu_latency_distribution = np.asarray(imu_latency_distribution, dtype=np.float32)
-        self._device = int(device)
+        self._device = None if device is None else int(device)  # None: the CUDA device that is current when the runtime is created
 
         rewards = reward_config["rewards"] if isinstance(reward_config, dict) else reward_config.rewards
         self._cfg_kwargs = dict(
@@ -201,10 +201,19 @@ class PupperV3Env:
         if self._runtime is not None:
             self._runtime.set_dr(sys_v)
 
+    def device_index(self) -> int:
+        """The CUDA device this env runs on (ctor argument, else the device that is current now: one process per GPU sets it once)."""
+        if self._device is None:
+            import torch
+            if not torch.cuda.is_available():
+                return 0  # EnvRuntime raises the loud "no CUDA device" error (there is no CPU fallback)
+            self._device = int(torch.cuda.current_device())
+        return self._device
+
     def _rt(self, n_envs: int):
         from . import runtime  # imports torch + loads the CUDA library; raises loudly if unavailable
         if self._runtime is None or self._runtime.n_envs != n_envs:
-            self._runtime = runtime.EnvRuntime(self.model_desc, self.env_cfg, n_envs, device=self._device)
+            self._runtime = runtime.EnvRuntime(self.model_desc, self.env_cfg, n_envs, device=self.device_index())
             self._runtime.set_dr(self._dr_sys)
         return self._runtime
 

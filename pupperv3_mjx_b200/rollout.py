@@ -33,7 +33,10 @@ class PolicyMLP(torch.nn.Module):
         if impl == "cuda":
             from . import runtime
             dev = torch.device(device)
-            self._kernel = runtime.PolicyRuntime(self.layers, device=dev.index or 0, precision=precision)
+            if dev.index is None:  # "cuda": the current device (one process per GPU sets it once), not device 0
+                dev = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+                device = dev
+            self._kernel = runtime.PolicyRuntime(self.layers, device=dev.index, precision=precision)
         self.weights = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(W, dtype=torch.float32, device=device), requires_grad=False) for W, _, _ in layers])
         self.biases = torch.nn.ParameterList([torch.nn.Parameter(torch.as_tensor(b, dtype=torch.float32, device=device), requires_grad=False) for _, b, _ in layers])
         self.acts = [utils.activation_fn_map(a) for _, _, a in layers]

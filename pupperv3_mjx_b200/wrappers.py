@@ -55,7 +55,7 @@ class TrainingEnv:
     def _runtime(self, n_envs: int):
         from . import runtime
         if self._rt is None or self._rt.n_envs != n_envs:
-            self._rt = runtime.EnvRuntime(self.env.model_desc, self.env.env_cfg, n_envs, device=self.env._device, episode=True)
+            self._rt = runtime.EnvRuntime(self.env.model_desc, self.env.env_cfg, n_envs, device=self.env.device_index(), episode=True)
             self._rt.set_dr(self._sys_v)
         return self._rt
 
