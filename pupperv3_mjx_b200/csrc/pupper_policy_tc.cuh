@@ -113,6 +113,23 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// Activations of the TF32 kernel.  The sigmoid family goes through the hardware tanh (tanh.approx.f32: ONE special-function
+// operation, absolute error ~5e-4 of a value bounded by 1 -- the size of the TF32 rounding the operands of the next layer get
+// anyway) instead of ex2 + rcp: the epilogue is bound by the special-function unit (81,920 activations per 128-row CTA), so
+// this halves its cost.  Everything else falls through to the float32-accurate forms of pupper_policy.cuh.
+__device__ __forceinline__ float tc_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float tc_act(float x) {
+  if (ACT == PUPPER_ACT_SWISH) { const float h = 0.5f * x; return fmaf(h, tc_tanh(h), h); }  // x sigmoid(x) = h + h tanh(h), h = x / 2
+  if (ACT == PUPPER_ACT_SIGMOID) return fmaf(0.5f, tc_tanh(0.5f * x), 0.5f);
+  if (ACT == PUPPER_ACT_TANH) return tc_tanh(x);
+  return policy_act<ACT>(x);
+}
+
 // Epilogue of one layer for this warp: quadrant q (rows 32 q + lane), 16-column groups h, h + 2, ...
 // `ready0` != 0 (warp-specialised kernel): after a group's 16 columns are in the A tile the warp arrives on the group's
 // mbarrier (ready0 + 8 g), so the MMA warp can start the next layer's k-steps on those columns at once.
@@ -127,7 +144,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams &p, const TcLayer &L,
     tc_ld16(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(16 * g), v);
     const int c0 = 16 * g;
 #pragma unroll
-    for (int i = 0; i < 16; i++) v[i] = policy_act<ACT>(v[i] + bias[c0 + i]);
+    for (int i = 0; i < 16; i++) v[i] = tc_act<ACT>(v[i] + bias[c0 + i]);
     if (!last) {
 #pragma unroll
       for (int i = 0; i < 4; i++)

@@ -844,7 +844,9 @@ def test_policy_tcgen05_path_is_used_and_matches_the_mma_sync_path(monkeypatch):
     a, b, c = pol_tc(x), pol_legacy(x), pol_tc2(x)
     torch.cuda.synchronize()
     assert torch.isfinite(a).all()
-    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=1e-4)  # TF32 rounding itself is ~1e-3
+    # same TF32 products; the tcgen05 kernel's sigmoid-family activations use the hardware tanh (abs error ~5e-4, the size of
+    # the TF32 operand rounding), the mma.sync kernel the float32-accurate forms
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=3e-3)
     assert torch.equal(a, c)  # same MMAs in the same order
     for _ in range(20):       # repeated launches: the mbarrier phases of every call start from scratch
         assert torch.equal(pol_tc2(x), c)
