@@ -37,6 +37,11 @@ def test_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.pupper_model_create(None, None, 0, None) == -1
     assert lib.pupper_step(None, 4, None, None, None, None, None, None, None) == -1
     assert lib.pupper_reset(None, 4, None, None, None, None, None, None, None) == -1
+    # rollout / policy entry points (include/pupper_policy.h): PUPPER_EINVAL before anything touches a device
+    assert lib.pupper_rollout(None, None, 4, 2, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pupper_rollout_timeouts(None) == -1
+    assert lib.pupper_policy_forward(None, 4, None, None, None) == -1
+    assert lib.pupper_policy_forward_record(None, 4, None, None, None, None) == -1
     env = common.make_env()
     rows = (C.c_int32 * 14)()
     assert lib.pupper_state_rows(C.byref(env.env_cfg), rows) == 0
