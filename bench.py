@@ -369,9 +369,10 @@ def run_cuda(args):
                      "note": "the step is instruction-issue bound, not HBM bound (DESIGN.md); see fp32"},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (H * abi.OBS_DIM + 2) * 4,
-                "steps": e2e_steps, "note": "EnvRuntime.step_host: pinned host action in (one range: read by the kernel over PCIe, no separate copy; pipelined ranges: H2D copies), "
-                          "obs+reward+done copied out to pinned host memory, host waits every step; "
-                          f"{max(1, min(8, n // 16384))} pipelined env range(s); the zero-copy device path (`value`) is the product number"},
+                "steps": e2e_steps, "note": "EnvRuntime.step_host: HOST buffers in and out, the host waits for every step's results; one kernel launch per "
+                          "step and nothing else -- the kernel reads the pinned host action over PCIe (h2d bytes) and stores obs / reward / done "
+                          "into the pinned host result buffer itself (d2h bytes; PupperStepOut.obs_copy), so the transfers are inside the timed "
+                          "region and overlap the CTAs still computing; the device-resident path (`value`) is the product number"},
         "gpu_launches": launches,
         "ms_per_step_quantiles": {"p50": float(np.quantile(per_step, 0.5)), "p90": float(np.quantile(per_step, 0.9)),
                                   "max": float(per_step.max()), "note": "rank 0; steps in which an env takes a rare solver path run longer"},

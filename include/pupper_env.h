@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PUPPER_ABI_VERSION 3
+#define PUPPER_ABI_VERSION 4
 
 /* Fixed topology of the supported robot family: world + base + 4 legs x 3 links. */
 #define PUPPER_NBODY 14
@@ -258,6 +258,12 @@ typedef struct PupperStepOut {
    *         (D = 0 past the active contacts)
    * (oracle: OracleDebug.efc_D / efc_aref; mjx constraint.py make_constraint) */
   float *dbg_efc;        /* [n_envs][44][2] */
+  /* optional (NULL to skip) second destination of the step's observation rows, [n_envs][observation_history * 36], 16-byte
+   * aligned: written by pupper_step at the end of the kernel, after the auto-reset block (so it equals state->obs after
+   * the call), in 512-byte pieces per warp.  Meant for mapped pinned HOST memory: together with reward / done pointing
+   * there too, a host-resident policy gets the step's results without a device-to-host copy being launched after the kernel
+   * (the stores travel over PCIe while other CTAs are still computing).  pupper_reset ignores it. */
+  float *obs_copy;
 } PupperStepOut;
 
 /* External randoms (optional; NULL = every draw is made in-kernel with threefry2x32 from state->rng).

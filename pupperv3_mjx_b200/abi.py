@@ -16,7 +16,7 @@ import numpy as np
 
 from .mjcf import CompiledModel, UnsupportedModelError
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 NBODY, NQ, NV, NU, NLEG, NSPHERE, NSITE = 14, 19, 18, 12, 4, 8, 5
 MAX_BOX, MAX_CON, MAX_PAIRS, MAX_LAT = 32, 8, 8, 8  # storage bounds of the header's tables
 KERNEL_MAX_CON, KERNEL_MAX_PAIRS = 5, 4  # what the CUDA path accepts (include/pupper_env.h PUPPER_KERNEL_MAX_*)
@@ -167,7 +167,7 @@ DR_ROWS = {"friction": 1, "kp": 1, "kd": 1, "base_ipos": 3, "body_inertia": 39, 
 class PupperStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "reward", "done", "metrics", "dbg_x_pos", "dbg_x_rot", "dbg_xd_vel", "dbg_xd_ang",
-        "dbg_qfrc_actuator", "dbg_contact_dist", "dbg_contact_geom", "dbg_site_xpos", "dbg_qacc", "dbg_solver", "dbg_efc")]
+        "dbg_qfrc_actuator", "dbg_contact_dist", "dbg_contact_geom", "dbg_site_xpos", "dbg_qacc", "dbg_solver", "dbg_efc", "obs_copy")]
 
 
 class PupperRand(C.Structure):

@@ -711,6 +711,20 @@ __device__ __forceinline__ void env_body(const KParams &p, BlockShared &sh, cons
   if (k == 0) { if (valid) at_step(io.reward, p.n_envs)[e] = reward; if (valid) at_step(io.done, p.n_envs)[e] = fdone; if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC] = total_dist; }
 #pragma unroll
   for (int q = 0; q < PUPPER_NREWARD; q++) if ((q & 3) == k) if (valid) p.out.metrics[(size_t)e * PUPPER_NMETRIC + 1 + q] = rw[q];
+
+  // ---- optional second copy of the observation rows (PupperStepOut.obs_copy; mapped pinned host memory) --------------------
+  // The warp's 8 envs are 8 consecutive rows: one contiguous block, copied in 16-byte pieces (512 bytes per warp instruction)
+  // after everything that writes obs (get_obs, the auto-reset restore).
+  if (p.out.obs_copy) {
+    __syncwarp(qm);
+    const int w4 = H * (PUPPER_OBS_DIM / 4);  // 16-byte pieces per row
+    const int e_w = block * kEnvsPerBlock + (tid >> 5) * 8;
+    const int total = min(8, p.n_envs - e_w) * w4;
+    const float4 *src = reinterpret_cast<const float4 *>(p.st.obs + (size_t)e_w * H * PUPPER_OBS_DIM);
+    float4 *dst = reinterpret_cast<float4 *>(p.out.obs_copy + (size_t)e_w * H * PUPPER_OBS_DIM);
+#pragma unroll 1
+    for (int i = lane; i < total; i += 32) dst[i] = src[i];
+  }
 }
 
 template <bool RESET, bool DBG>
@@ -889,6 +903,7 @@ static int check_common(const PupperModel *model, int n_envs, const PupperDR *dr
       !st->last_vel || !st->command || !st->desired_world_z || !st->last_contact || !st->feet_air_time || !st->step || !st->kick || !st->obs)
     return PUPPER_EINVAL;
   if (!out->reward || !out->done || !out->metrics) return PUPPER_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(out->obs_copy) & 15) != 0 || (reinterpret_cast<uintptr_t>(st->obs) & 15) != 0) return PUPPER_EINVAL;
   if (dr && (dr->stride < n_envs || !dr->friction || !dr->kp || !dr->kd || !dr->base_ipos || !dr->body_inertia || !dr->body_mass)) return PUPPER_EINVAL;
   if (ep && (ep->stride < n_envs || !ep->first_qpos || !ep->first_qvel || !ep->first_warmstart || !ep->first_obs || !ep->steps ||
              !ep->truncation || !ep->sum_reward || !ep->length || !ep->sum_metrics || !ep->episode_done))

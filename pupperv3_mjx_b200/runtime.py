@@ -394,10 +394,11 @@ class EnvRuntime:
         (the ``packed_outputs`` layout, pinned) out.  Returns the object to ``.synchronize()`` on before reading ``h_out`` (the
         caller's stream for one range, an event for the pipelined case).
 
-        Large batches are cut into ``chunks`` contiguous env ranges that are pipelined over three streams (actions in,
-        step kernels in order, observations out), so the PCIe transfers of one range overlap the kernel of the next: at
-        65,536 envs the 19 MB of observations per step cost about as much as the step itself.  Small batches (the step
-        is latency bound and would not get shorter by splitting) take one chunk on the current stream."""
+        Default: ONE kernel launch and nothing else.  Pinned host memory is device-addressable, so the kernel reads the actions
+        from ``h_action`` and stores obs (``PupperStepOut.obs_copy``), reward and done into ``h_out`` itself; CTAs finish at
+        different times, so the PCIe traffic overlaps the computation without any copy being enqueued.  ``chunks`` > 1 (or
+        ``PUPPER_HOST_OUT_COPY=1``) selects the older path: contiguous env ranges pipelined over three streams (actions in,
+        step kernels in order, observations out) with explicit copies."""
         n = self.n_envs
         w = self.cfg.observation_history * abi.OBS_DIM
         if h_action.dtype != torch.float32 or h_action.numel() != n * abi.NU or h_out.dtype != torch.float32 or h_out.numel() != n * (w + 2):
@@ -413,7 +414,11 @@ class EnvRuntime:
                                   "synchronous and serialises the three-stream pipeline)")
             ok.add((t.data_ptr(), t.numel()))
         if chunks is None:
-            chunks = max(1, min(8, n // 16384))
+            # zero-copy results (below): one launch at every size -- the CTAs' stores to the pinned buffer are spread over the
+            # kernel's run time, which pipelines the PCIe traffic by itself (65,536 envs: 9.25e7 env-steps/s against 8.0e7 for
+            # four pipelined ranges with copies).  The ranges remain for PUPPER_HOST_OUT_COPY=1 and explicit `chunks`.
+            zero_copy = os.environ.get("PUPPER_HOST_OUT_COPY", "0") != "1"
+            chunks = int(os.environ.get("PUPPER_HOST_CHUNKS", "0")) or (1 if zero_copy else max(1, min(8, n // 16384)))
         if not hasattr(self, "_d_act"):
             if self.guard_rows or self.dbg:
                 raise PupperError("step_host is the production path: no guard rows, no debug taps")
@@ -421,6 +426,7 @@ class EnvRuntime:
             self._s_in, self._s_out = torch.cuda.Stream(self.device), torch.cuda.Stream(self.device)
             self._done_ev = torch.cuda.Event()
             self._zero_copy_action = os.environ.get("PUPPER_HOST_ACTION_COPY", "0") != "1"
+            self._zero_copy_out = os.environ.get("PUPPER_HOST_OUT_COPY", "0") != "1"
         cur = torch.cuda.current_stream(self.device)
         if chunks <= 1:
             # latency path: three enqueues on the caller's stream; the stream itself is the thing to wait on
@@ -435,13 +441,27 @@ class EnvRuntime:
             else:
                 self._d_act.copy_(h_action.view(n, abi.NU), non_blocking=True)
                 act_ptr = self._d_act.data_ptr()
+            # Results the same way: obs (PupperStepOut.obs_copy), reward and done are stored by the kernel straight into the
+            # pinned h_out (obs | reward | done), so no device-to-host copy is launched after it; the stores of the CTAs that
+            # finish first travel over PCIe while the others still compute.  PUPPER_HOST_OUT_COPY=1 restores the copy.
+            out = self.out
+            if self._zero_copy_out:
+                key = ("host", h_out.data_ptr())
+                out = self._out_variants.get(key)
+                if out is None:
+                    out = abi.PupperStepOut()
+                    C.memmove(C.byref(out), C.byref(self.out), C.sizeof(out))
+                    base = h_out.data_ptr()
+                    out.obs_copy, out.reward, out.done = base, base + 4 * n * w, base + 4 * n * (w + 1)
+                    self._out_variants[key] = out
             rc = self.lib.pupper_step(self._model, n, C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
-                                      act_ptr, None, C.byref(self.out), C.byref(self.episode) if self.episode else None,
+                                      act_ptr, None, C.byref(out), C.byref(self.episode) if self.episode else None,
                                       cur.cuda_stream)
             if rc != 0:
                 _check(self.lib, rc, "pupper_step")
             self.launches += 1
-            h_out.view(-1).copy_(self._out_pack, non_blocking=True)
+            if not self._zero_copy_out:
+                h_out.view(-1).copy_(self._out_pack, non_blocking=True)
             return cur
         done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
         ha, flat = h_action.view(n, abi.NU), h_out.view(-1)
