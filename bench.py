@@ -151,8 +151,8 @@ def load_counters():
     a `--set full` capture).  They are only quoted when they were captured from the library build that is loaded now."""
     try:
         c = json.load(open(COUNTERS))
-        stamp = open(os.path.join(ROOT, "pupperv3_mjx_b200", "libpupper_env.so.stamp")).read().strip()
-        c["matches_loaded_library"] = (c.get("lib_digest") == stamp)
+        import __graft_entry__ as g
+        c["matches_loaded_library"] = (c.get("kernel_digest") == g.kernel_digest())
         return c
     except Exception:
         return {"matches_loaded_library": False}

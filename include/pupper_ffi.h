@@ -47,17 +47,29 @@ int pupper_dr_blob_pack(int n_envs, const float *friction /*[n]*/, const float *
  * handle registered for the device its stream belongs to.  No process-global "current model". */
 int pupper_ffi_register_model(int device, const PupperModel *model, const PupperEnvCfg *cfg);
 int pupper_ffi_unregister_model(int device);
+/* the policy of the rollout handlers, same convention (a handle of pupper_policy_create, include/pupper_policy.h; in_dim /
+ * out_dim are its first layer's input and last layer's output width) */
+struct PupperPolicy;
+int pupper_ffi_register_policy(int device, const struct PupperPolicy *policy, int in_dim, int out_dim);
+int pupper_ffi_unregister_policy(int device);
 
 /* ---- XLA FFI handlers (typed-FFI C ABI: XLA_FFI_Error* handler(XLA_FFI_CallFrame*)) ---------------------------------------
  * PupperStepFfi   args: action f32[n,12], state blob, DR blob (or 0 elements), episode blob (or 0), rand blob (or 0)
  *                 rets: state blob (alias of arg 1), reward f32[n], done f32[n], metrics f32[n,19], episode blob (alias of arg 3)
  * PupperResetFfi  args: keys u32[n,2], DR blob (or 0), rand blob (or 0)
  *                 rets: state blob, reward f32[n], done f32[n], metrics f32[n,19], episode blob (or 0 elements)
+ * PupperPolicyFfi  args: obs f32[n, in]                         rets: action f32[n, out]        (pupper_policy_forward)
+ * PupperRolloutFfi args: state blob, DR blob (or 0 elements), episode blob (or 0)
+ *                  rets: state blob (alias of arg 0), episode blob (alias of arg 2), obs f32[T,n,H*36], action f32[T,n,12],
+ *                        reward f32[T,n], done f32[T,n], metrics f32[n,19] of the last step    (pupper_rollout: the whole unroll
+ *                        that brax.training.acting.generate_unroll scans, as one custom call; T and n come from the action result)
  * A result that XLA did not alias to its argument is first filled with a device copy of the argument. */
 struct XLA_FFI_CallFrame;
 struct XLA_FFI_Error;
 struct XLA_FFI_Error *PupperStepFfi(struct XLA_FFI_CallFrame *call_frame);
 struct XLA_FFI_Error *PupperResetFfi(struct XLA_FFI_CallFrame *call_frame);
+struct XLA_FFI_Error *PupperPolicyFfi(struct XLA_FFI_CallFrame *call_frame);
+struct XLA_FFI_Error *PupperRolloutFfi(struct XLA_FFI_CallFrame *call_frame);
 
 #ifdef __cplusplus
 }

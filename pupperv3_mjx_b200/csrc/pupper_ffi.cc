@@ -11,12 +11,15 @@
 #include "xla_ffi_stub.h"
 #endif
 #include "../../include/pupper_ffi.h"
+#include "../../include/pupper_policy.h"
 
 namespace {
 
 constexpr int kMaxDevices = 64;
 struct Registered { const PupperModel *model; PupperEnvCfg cfg; bool on; };
 Registered g_models[kMaxDevices];
+struct RegisteredPolicy { const PupperPolicy *policy; int in_dim, out_dim; bool on; };
+RegisteredPolicy g_policies[kMaxDevices];
 std::mutex g_mu;
 
 constexpr int kDrRows = 1 + 1 + 1 + 3 + 39 + 13;                                     // 58
@@ -51,6 +54,22 @@ XLA_FFI_Error *context(XLA_FFI_CallFrame *cf, cudaStream_t *stream, Registered *
   std::lock_guard<std::mutex> lock(g_mu);
   if (!g_models[dev].on) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper: no model registered for this device (pupper_ffi_register_model)");
   *reg = g_models[dev];
+  return nullptr;
+}
+
+// The stream XLA hands out, the device the call runs on and the policy registered for it.
+XLA_FFI_Error *policy_context(XLA_FFI_CallFrame *cf, cudaStream_t *stream, RegisteredPolicy *reg) {
+  XLA_FFI_Stream_Get_Args s;
+  memset(&s, 0, sizeof(s));
+  s.struct_size = sizeof(s);
+  s.ctx = cf->ctx;
+  if (XLA_FFI_Error *e = cf->api->XLA_FFI_Stream_Get(&s)) return e;
+  *stream = static_cast<cudaStream_t>(s.stream);
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return fail(cf, XLA_FFI_Error_Code_INTERNAL, "pupper: no current CUDA device");
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (!g_policies[dev].on) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper: no policy registered for this device (pupper_ffi_register_policy)");
+  *reg = g_policies[dev];
   return nullptr;
 }
 
@@ -162,6 +181,81 @@ int pupper_ffi_unregister_model(int device) {
   std::lock_guard<std::mutex> lock(g_mu);
   g_models[device].on = false;
   return PUPPER_OK;
+}
+
+int pupper_ffi_register_policy(int device, const PupperPolicy *policy, int in_dim, int out_dim) {
+  if (device < 0 || device >= kMaxDevices || !policy || in_dim < 1 || out_dim < 1) return PUPPER_EINVAL;
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_policies[device] = RegisteredPolicy{policy, in_dim, out_dim, true};
+  return PUPPER_OK;
+}
+int pupper_ffi_unregister_policy(int device) {
+  if (device < 0 || device >= kMaxDevices) return PUPPER_EINVAL;
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_policies[device].on = false;
+  return PUPPER_OK;
+}
+
+XLA_FFI_Error *PupperPolicyFfi(XLA_FFI_CallFrame *cf) {
+  if (cf->stage != XLA_FFI_ExecutionStage_EXECUTE) return nullptr;
+  if (cf->args.size != 1 || cf->rets.size != 1) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_policy: expected 1 argument and 1 result");
+  const XLA_FFI_Buffer *obs = static_cast<XLA_FFI_Buffer *>(cf->args.args[0]), *action = static_cast<XLA_FFI_Buffer *>(cf->rets.rets[0]);
+  if (obs->rank != 2 || action->rank != 2 || obs->dtype != XLA_FFI_DataType_F32 || action->dtype != XLA_FFI_DataType_F32 || obs->dims[0] != action->dims[0])
+    return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_policy: obs must be f32[n, in] and the result f32[n, out]");
+  cudaStream_t stream;
+  RegisteredPolicy reg;
+  if (XLA_FFI_Error *e = policy_context(cf, &stream, &reg)) return e;
+  if (obs->dims[1] != reg.in_dim || action->dims[1] != reg.out_dim)
+    return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_policy: widths differ from the registered policy's");
+  const int rc = pupper_policy_forward(reg.policy, (int)obs->dims[0], static_cast<const float *>(obs->data), static_cast<float *>(action->data), stream);
+  return rc == PUPPER_OK ? nullptr : fail(cf, XLA_FFI_Error_Code_INTERNAL, pupper_strerror(rc));
+}
+
+XLA_FFI_Error *PupperRolloutFfi(XLA_FFI_CallFrame *cf) {
+  if (cf->stage != XLA_FFI_ExecutionStage_EXECUTE) return nullptr;
+  if (cf->args.size != 3 || cf->rets.size != 7) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: expected 3 arguments and 7 results");
+  auto arg = [&](int i) { return static_cast<XLA_FFI_Buffer *>(cf->args.args[i]); };
+  auto ret = [&](int i) { return static_cast<XLA_FFI_Buffer *>(cf->rets.rets[i]); };
+  const XLA_FFI_Buffer *state_in = arg(0), *dr_b = arg(1), *ep_in = arg(2);
+  const XLA_FFI_Buffer *state_out = ret(0), *ep_out = ret(1), *t_obs = ret(2), *t_act = ret(3), *t_rew = ret(4), *t_done = ret(5), *metrics = ret(6);
+  if (t_act->rank != 3 || t_act->dims[2] != PUPPER_NU || t_act->dtype != XLA_FFI_DataType_F32)
+    return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: the action trajectory must be f32[T, n, 12]");
+  const int T = (int)t_act->dims[0], n = (int)t_act->dims[1];
+  cudaStream_t stream;
+  Registered reg;
+  RegisteredPolicy pol;
+  if (XLA_FFI_Error *e = context(cf, &stream, &reg)) return e;
+  if (XLA_FFI_Error *e = policy_context(cf, &stream, &pol)) return e;
+  const int64_t w = (int64_t)reg.cfg.observation_history * PUPPER_OBS_DIM;
+  if (T < 1 || n < 1 || elements(t_obs) != (int64_t)T * n * w || elements(t_rew) != (int64_t)T * n || elements(t_done) != (int64_t)T * n ||
+      elements(metrics) != (int64_t)n * PUPPER_NMETRIC)
+    return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: trajectory / metrics results have the wrong size");
+  if (elements(state_in) != pupper_state_blob_words(&reg.cfg, n)) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: state blob has the wrong size");
+  if (XLA_FFI_Error *e = carry(cf, state_in, state_out, stream)) return e;
+  PupperState st;
+  pupper_state_blob_bind(&reg.cfg, n, state_out->data, &st);
+  PupperDR dr, *drp = nullptr;
+  if (elements(dr_b) > 0) {
+    if (elements(dr_b) != pupper_dr_blob_words(n)) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: DR blob has the wrong size");
+    pupper_dr_blob_bind(n, dr_b->data, &dr);
+    drp = &dr;
+  }
+  PupperEpisode ep, *epp = nullptr;
+  if (elements(ep_in) > 0) {
+    if (elements(ep_in) != pupper_episode_blob_words(&reg.cfg, n)) return fail(cf, XLA_FFI_Error_Code_INVALID_ARGUMENT, "pupper_rollout: episode blob has the wrong size");
+    if (XLA_FFI_Error *e = carry(cf, ep_in, ep_out, stream)) return e;
+    pupper_episode_blob_bind(&reg.cfg, n, ep_out->data, &ep);
+    epp = &ep;
+  }
+  PupperStepOut out;
+  memset(&out, 0, sizeof(out));
+  float *rew = static_cast<float *>(t_rew->data), *dn = static_cast<float *>(t_done->data);
+  out.reward = rew + (size_t)(T - 1) * n;  // "the last step's" single-step outputs are the last trajectory slices themselves
+  out.done = dn + (size_t)(T - 1) * n;
+  out.metrics = static_cast<float *>(metrics->data);
+  const int rc = pupper_rollout(reg.model, pol.policy, n, T, drp, &st, &out, epp, static_cast<float *>(t_obs->data), static_cast<float *>(t_act->data),
+                                rew, dn, stream);
+  return rc == PUPPER_OK ? nullptr : fail(cf, XLA_FFI_Error_Code_INTERNAL, pupper_strerror(rc));
 }
 
 XLA_FFI_Error *PupperStepFfi(XLA_FFI_CallFrame *cf) {

@@ -98,6 +98,10 @@ def _lib():
     lib.PupperResetFfi.restype = C.c_void_p
     lib.PupperStepFfi.argtypes = [C.c_void_p]
     lib.PupperResetFfi.argtypes = [C.c_void_p]
+    for f in ("PupperPolicyFfi", "PupperRolloutFfi"):
+        getattr(lib, f).restype = C.c_void_p
+        getattr(lib, f).argtypes = [C.c_void_p]
+    lib.pupper_ffi_register_policy.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
     for f in ("pupper_state_blob_words", "pupper_dr_blob_words", "pupper_episode_blob_words", "pupper_rand_blob_words"):
         getattr(lib, f).restype = C.c_int64
     return lib
@@ -157,6 +161,14 @@ def test_handlers_validate_the_call_frame_without_a_gpu():
     assert "u32[n, 2]" in x.errors[-1][0]
     assert lib.PupperStepFfi(C.addressof(x.frame([b] * 5, [b] * 5, stage=1))) is None  # not the EXECUTE stage: no-op
     assert lib.pupper_ffi_register_model(0, None, None) == -1 and lib.pupper_ffi_unregister_model(99) == -1
+    # policy / rollout handlers
+    assert lib.PupperPolicyFfi(C.addressof(x.frame([b, b], [b]))) == 0xDEAD and "1 argument" in x.errors[-1][0]
+    assert lib.PupperPolicyFfi(C.addressof(x.frame([x.buf(one.ctypes.data, (4, 6))], [x.buf(one.ctypes.data, (2, 12))]))) == 0xDEAD  # row counts differ
+    assert "f32[n, in]" in x.errors[-1][0]
+    assert lib.PupperRolloutFfi(C.addressof(x.frame([b] * 2, [b] * 7))) == 0xDEAD and "3 arguments and 7 results" in x.errors[-1][0]
+    assert lib.PupperRolloutFfi(C.addressof(x.frame([b] * 3, [b] * 7))) == 0xDEAD and "f32[T, n, 12]" in x.errors[-1][0]  # action result is rank 2
+    assert lib.PupperRolloutFfi(C.addressof(x.frame([b] * 3, [b] * 7, stage=1))) is None
+    assert lib.pupper_ffi_register_policy(0, None, 72, 12) == -1 and lib.pupper_ffi_unregister_policy(99) == -1
 
 
 @pytest.mark.gpu
@@ -232,3 +244,59 @@ def test_reset_and_steps_through_the_ffi_handlers_match_the_runtime():
     fr = x.frame([B(a, (n, 12)), B(state, (state.numel(),)), B(drb, (drb.numel(),)), B(ep, (ep.numel(),)), B(empty, (0,))],
                  [B(state, (state.numel(),)), B(reward, (n,)), B(done, (n,)), B(metrics, (n, 19)), B(ep, (ep.numel(),))])
     assert lib.PupperStepFfi(C.addressof(fr)) == 0xDEAD and "no model registered" in x.errors[-1][0]
+
+
+@pytest.mark.gpu
+def test_policy_and_rollout_through_the_ffi_handlers_match_the_runtime():
+    """PupperPolicyFfi = pupper_policy_forward, PupperRolloutFfi = pupper_rollout on blobs: one custom call returns the
+    [T, n, ...] trajectory and the advanced state / episode blobs, equal to what the ctypes / torch path produces."""
+    torch = pytest.importorskip("torch")
+    from pupperv3_mjx_b200 import rollout
+    lib = _lib()
+    env = common.make_env()
+    env.set_episode_params(6, 1)
+    cfg = env.env_cfg
+    n, T = 136, 9
+    dev = torch.device("cuda", 0)
+    keys = common.env_keys(n)
+    rt = runtime.EnvRuntime(env.model_desc, cfg, n, episode=True)
+    d_keys = torch.from_numpy(keys.view(np.int32)).to(dev)
+    rt.reset(d_keys)
+    pol = rollout.PolicyMLP.random(env.observation_size, impl="cuda", precision=3, seed=7)
+    w = env.observation_size
+    assert lib.pupper_ffi_register_model(0, rt._model, C.byref(cfg)) == 0
+    assert lib.pupper_ffi_register_policy(0, pol._kernel._handle, w, 12) == 0
+    zeros = lambda *shape: torch.zeros(shape, dtype=torch.float32, device=dev)
+    x = FakeXla(stream=torch.cuda.current_stream().cuda_stream)
+    B = lambda t, dims, dt=F32: x.buf(t.data_ptr() if t.numel() else None, dims, dt)
+    # the policy alone
+    obs = torch.randn((n, w), device=dev)
+    act = zeros(n, 12)
+    assert lib.PupperPolicyFfi(C.addressof(x.frame([B(obs, (n, w))], [B(act, (n, 12))]))) is None, x.errors
+    torch.cuda.synchronize()
+    assert torch.equal(act, pol(obs))
+    assert lib.PupperPolicyFfi(C.addressof(x.frame([B(obs[:, :8].contiguous(), (n, 8))], [B(act, (n, 12))]))) == 0xDEAD  # wrong width
+    # reset into blobs, then one unroll as ONE custom call against the runtime's rollout
+    state = zeros(int(lib.pupper_state_blob_words(C.byref(cfg), n)))
+    ep = zeros(int(lib.pupper_episode_blob_words(C.byref(cfg), n)))
+    reward, done, metrics, empty = zeros(n), zeros(n), zeros(n * 19), zeros(0)
+    fr = x.frame([B(d_keys, (n, 2), U32), B(empty, (0,)), B(empty, (0,))],
+                 [B(state, (state.numel(),)), B(reward, (n,)), B(done, (n,)), B(metrics, (n, 19)), B(ep, (ep.numel(),))])
+    assert lib.PupperResetFfi(C.addressof(fr)) is None, x.errors
+    t_obs, t_act, t_rew, t_done = zeros(T, n, w), zeros(T, n, 12), zeros(T, n), zeros(T, n)
+    fr = x.frame([B(state, (state.numel(),)), B(empty, (0,)), B(ep, (ep.numel(),))],
+                 [B(state, (state.numel(),)), B(ep, (ep.numel(),)), B(t_obs, (T, n, w)), B(t_act, (T, n, 12)), B(t_rew, (T, n)), B(t_done, (T, n)),
+                  B(metrics, (n, 19))])
+    assert lib.PupperRolloutFfi(C.addressof(fr)) is None, x.errors
+    r_obs, r_act, r_rew, r_done = zeros(T, n, w), zeros(T, n, 12), zeros(T, n), zeros(T, n)
+    rt.rollout(pol._kernel, r_obs, r_act, r_rew, r_done)
+    torch.cuda.synchronize()
+    for a, b, name in ((t_obs, r_obs, "obs"), (t_act, r_act, "action"), (t_rew, r_rew, "reward"), (t_done, r_done, "done")):
+        assert torch.equal(a, b), name
+    assert float(t_done.sum()) > 0  # episodes of 6 steps ended inside the unroll
+    st = abi.PupperState()
+    lib.pupper_state_blob_bind(C.byref(cfg), n, C.c_void_p(state.data_ptr()), C.byref(st))
+    off = (st.obs - state.data_ptr()) // 4
+    assert torch.equal(state[off: off + n * w].view(n, w), rt.obs)
+    assert torch.equal(metrics.view(n, 19), rt.metrics)
+    assert lib.pupper_ffi_unregister_policy(0) == 0 and lib.pupper_ffi_unregister_model(0) == 0

@@ -70,8 +70,9 @@ line = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "line_hist.py
                       capture_output=True, text=True)
 line_txt = line.stdout if line.returncode == 0 else "(library rebuilt since the capture)"
 # per-launch counters quoted by bench.py (only when the loaded library is the one that was profiled)
-stamp = open(os.path.join(ROOT, "pupperv3_mjx_b200", "libpupper_env.so.stamp")).read().strip()
-counters = {"lib_digest": stamp, "source": f"gpurun_out/{tag}_prof_<envs>.ncu-rep (ncu --set full, launch #110 of bench.py --steps 20 --warmup 3)"}
+sys.path.insert(0, ROOT)
+import __graft_entry__ as _g
+counters = {"kernel_digest": _g.kernel_digest(), "source": f"gpurun_out/{tag}_prof_<envs>.ncu-rep (ncu --set full, launch #110 of bench.py --steps 20 --warmup 3)"}
 for n in (4096, 65536):
     hdr, units, vals = raw(os.path.join(G, f"{tag}_prof_{n}.ncu-rep"))
     d = dict(zip(hdr, vals)); u = dict(zip(hdr, units))
