@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kBlock, PUPPER_MIN_BLOCKS) rollout_kernel(cons
       int spins = 0;
       while (ld_acquire_gpu(ro.group_step + blockIdx.x) < (int)blockIdx.y) {
         __nanosleep(100);
-        if (++spins > (1 << 24)) { atomicAdd(ro.group_step + gridDim.x, 1); break; }  // never in practice: do not hang the device
+        if (++spins > (1 << 18)) { atomicAdd(ro.group_step + gridDim.x, 1); break; }  // ~0.3 s; never in practice: do not hang the device (pupper_rollout_timeouts counts it)
       }
     }
   }
