@@ -65,10 +65,32 @@ def record(state):
     return r
 
 
-def rollout(kw_over, n, steps, seed, action_scale=0.5, tamper=None):
+def keys_on_boxes(n, seed, start_range):
+    """Env keys whose start pose puts a foot on one of the 2 cm wide box strips (found with this repo's oracle reset, which the
+    other fixtures pin against the reference's reset): otherwise a handful of robots dropped at random almost never touch one."""
+    from oracle import oracle
+    from pupperv3_mjx_b200 import domain_randomization as own_dr
+    r = start_range
+    env = common.make_env(path=common.obstacle_tree(10, seed=0),
+                          start_position_config=own_dr.StartPositionRandomization(x_min=-r, x_max=r, y_min=-r, y_max=r, z_min=0.18, z_max=0.24))
+    cand = common.env_keys(6000, seed)
+    O = oracle.Oracle(env.model_desc, env.env_cfg, "f32")
+    O.reset(cand, debug=True)
+    feet = np.asarray(O.debug["site_xpos"]).reshape(len(cand), -1, 3)[:, 1:5, :2]  # the four foot sites, xy
+    m = env._model
+    hit = np.zeros(len(cand), bool)
+    for b in range(len(m.box_geomid)):
+        local = (feet - np.asarray(m.box_pos)[b, :2]) @ np.asarray(m.box_mat)[b][:2, :2]  # world -> box frame (rotation about z)
+        hit |= ((np.abs(local[..., 0]) < 0.012) & (np.abs(local[..., 1]) < 2.9)).any(1)
+    idx = np.flatnonzero(hit)[:n]
+    assert len(idx) == n, len(idx)
+    return cand[idx]
+
+
+def rollout(kw_over, n, steps, seed, action_scale=0.5, tamper=None, keys=None):
     """n independent envs x (reset + steps).  Returns dict of arrays [steps + 1, n, ...] (index 0 = after reset)."""
     env = environment.PupperV3Env(**ref_kwargs(**kw_over))
-    keys = common.env_keys(n, seed)
+    keys = common.env_keys(n, seed) if keys is None else keys
     states = [env.reset(jp.array(keys[i])) for i in range(n)]
     if tamper:
         states = [tamper(s) for s in states]
@@ -82,6 +104,19 @@ def rollout(kw_over, n, steps, seed, action_scale=0.5, tamper=None):
     return out
 
 
+def obstacle_xml():
+    """The reference's own terrain generator (obstacles.add_boxes_to_model, obstacles.py:16-57) on the reference's model, written to
+    a scratch file because PupperV3Env takes a path: 10 boxes of 6 m x 2 cm x 2 cm, random.seed(0)."""
+    import random
+    import tempfile
+    import xml.etree.ElementTree as ET
+    random.seed(0)
+    tree = obstacles.add_boxes_to_model(ET.ElementTree(ET.fromstring(open(REF_XML).read())), n_boxes=10, x_range=(-5, 5), y_range=(-5, 5), height=0.02, length=6.0)
+    path = os.path.join(tempfile.mkdtemp(), "pupper_with_boxes.xml")
+    tree.write(path)
+    return path
+
+
 CASES = {
     # name: (ctor overrides, envs, steps, seed, action scale)
     "flat": (dict(), 6, 130, 0, 0.5),                       # crosses resample_velocity_step = 100; kicks at p = 0.04
@@ -89,6 +124,9 @@ CASES = {
     "stand": (dict(resample_velocity_step=20, kick_probability=0.1), 4, 90, 7, 0.15),  # small actions: every env lives past a command / orientation resampling
     "noimu_lat4": (dict(use_imu=False, latency_distribution=jp.array([0.1, 0.2, 0.3, 0.4]), imu_latency_distribution=jp.array([0.2, 0.3, 0.5]),
                         observation_history=3), 3, 25, 5, 0.5),
+    # the obstacle terrain (geom ids shift by the 10 boxes: collision-reward geom lists, sphere-box contacts under the feet and knees)
+    # (start poses spread over +-4 m so that several robots come down on a box strip; small actions so that they stay up on it)
+    "boxes": (dict(path="<obstacles>", kick_probability=0.1, start_range=4.0), 8, 40, 11, 0.3),
 }
 
 
@@ -98,12 +136,23 @@ def main():
     for prec in ("f32",):
         benv.PHYSICS_PRECISION = prec
         for name, (over, n, steps, seed, scale) in CASES.items():
-            data = rollout(over, n, steps, seed, scale)
+            run_over = dict(over)
+            if run_over.get("path") == "<obstacles>":
+                run_over["path"] = obstacle_xml()
+            keys = None
+            if "start_range" in run_over:
+                r = run_over.pop("start_range")
+                run_over["start_position_config"] = domain_randomization.StartPositionRandomization(x_min=-r, x_max=r, y_min=-r, y_max=r, z_min=0.18, z_max=0.24)
+                keys = keys_on_boxes(n, seed, r)
+            data = rollout(run_over, n, steps, seed, scale, keys=keys)
             path = os.path.join(HERE, f"ref_{name}.npz")
             np.savez_compressed(path, **data)
             meta["cases"][name] = {"envs": n, "steps": steps, "seed": seed, "action_scale": scale, "physics": "oracle " + prec,
                                    "overrides": {k: (np.asarray(v).tolist() if not isinstance(v, (int, float, bool)) else v) for k, v in over.items()},
                                    "dones": int(data["done"].sum()), "kicks": int((np.abs(data["info_kick"]).sum(-1) > 0).sum())}
+            if over.get("path") == "<obstacles>":
+                meta["cases"][name]["obstacles"] = {"n_boxes": 10, "seed": 0}
+                del meta["cases"][name]["overrides"]["path"]
             print(name, {k: v.shape for k, v in list(data.items())[:3]}, meta["cases"][name])
 
     # ---- what the constructor derives from the model (environment.py:165-244): ids, start pose, time steps ------------------

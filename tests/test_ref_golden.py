@@ -25,6 +25,12 @@ def case_env(name):
     for k in ("latency_distribution", "imu_latency_distribution"):
         if k in over:
             over[k] = np.asarray(over[k], np.float32)
+    if "start_range" in over:
+        r = over.pop("start_range")
+        over["start_position_config"] = dr.StartPositionRandomization(x_min=-r, x_max=r, y_min=-r, y_max=r, z_min=0.18, z_max=0.24)
+    ob = META["cases"][name].get("obstacles")  # the reference ran on obstacles.add_boxes_to_model's terrain (same Mersenne stream here)
+    if ob:
+        over["path"] = common.obstacle_tree(ob["n_boxes"], seed=ob["seed"])
     return common.make_env(**over)
 
 
