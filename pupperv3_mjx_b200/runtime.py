@@ -453,6 +453,8 @@ class EnvRuntime:
                     C.memmove(C.byref(out), C.byref(self.out), C.sizeof(out))
                     base = h_out.data_ptr()
                     out.obs_copy, out.reward, out.done = base, base + 4 * n * w, base + 4 * n * (w + 1)
+                    if len(self._out_variants) > 4096:
+                        self._out_variants.clear()
                     self._out_variants[key] = out
             rc = self.lib.pupper_step(self._model, n, C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state),
                                       act_ptr, None, C.byref(out), C.byref(self.episode) if self.episode else None,
