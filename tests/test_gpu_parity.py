@@ -457,6 +457,40 @@ def test_full_size_properties():
     assert np.array_equal(h2.get("qpos"), q) and np.array_equal(h2.get("obs"), obs)
 
 
+def test_full_size_host_path_is_one_launch_and_exact():
+    """BASELINE full size through the host-buffer path: EnvRuntime.step_host is ONE kernel launch (the kernel reads the pinned
+    actions and stores obs / reward / done into the pinned result buffer itself, PupperStepOut.obs_copy) and delivers exactly
+    what the device-buffer step leaves on the device; full DR, fused episode block, short episodes (auto-resets inside)."""
+    import torch
+    from pupperv3_mjx_b200 import abi, domain_randomization as dr, prng, runtime
+    n = 65536
+    env = common.make_env()
+    env.set_episode_params(4, 1)
+    sys_v, _ = dr.domain_randomize(env.sys, prng.split(prng.PRNGKey(2), n))
+    keys = torch.from_numpy(common.env_keys(n).view(np.int32)).cuda()
+    w = env.env_cfg.observation_history * abi.OBS_DIM
+    rts = []
+    for _ in range(2):
+        rt = runtime.EnvRuntime(env.model_desc, env.env_cfg, n, episode=True)
+        rt.set_dr(sys_v)
+        rt.reset(keys)
+        rts.append(rt)
+    dev_rt, host_rt = rts
+    h_out = torch.empty(n * (w + 2), dtype=torch.float32).pin_memory()
+    ndone = 0.0
+    for t in range(6):
+        a = common.actions(n, t)
+        dev_rt.step(torch.from_numpy(a).cuda())
+        l0 = host_rt.launches
+        host_rt.step_host(torch.from_numpy(a).pin_memory(), h_out).synchronize()
+        assert host_rt.launches - l0 == 1
+        ref = dev_rt.packed_outputs().cpu().numpy()
+        np.testing.assert_array_equal(h_out.numpy(), ref, err_msg=f"step {t}")
+        ndone += float(h_out[n * (w + 1):].sum())
+    assert ndone >= n  # episodes of 4 steps ended: the auto-reset restore went through obs_copy too
+    assert torch.equal(host_rt.obs, dev_rt.obs)
+
+
 def test_public_api_reset_step_and_wrappers():
     from pupperv3_mjx_b200 import wrappers
     import functools
