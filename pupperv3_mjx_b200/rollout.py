@@ -126,3 +126,49 @@ class RolloutCollector:
         else:
             self._unroll()
         return {"obs": self.obs, "action": self.action, "reward": self.reward, "done": self.done}
+
+
+def check_export_against_env(policy_dict: Dict, env) -> None:
+    """The deployment contract of an exported policy (reference ``export.py:65-79``: the JSON carries the action scale, PD gains,
+    default pose, joint limits, IMU use and observation history the policy was trained with): raise if the env it is about to
+    drive was built with other values -- the controller on the robot would interpret the same numbers differently."""
+    import math
+    c, d = env.env_cfg, env.model_desc
+    want = {"observation_history": c.observation_history, "use_imu": bool(c.use_imu), "action_scale": c.action_scale,
+            "kp": d.act_gain[0], "kd": -d.act_bias2[0], "maximum_pitch_command": c.maximum_pitch_command,
+            "maximum_roll_command": c.maximum_roll_command}
+    for k, v in want.items():
+        if k in policy_dict and not (policy_dict[k] == v or (isinstance(v, float) and math.isclose(float(policy_dict[k]), v, rel_tol=1e-6, abs_tol=1e-9))):
+            raise ValueError(f"exported policy has {k} = {policy_dict[k]!r}, the env was built with {v!r}")
+    for k, arr in (("default_joint_pos", c.default_pose), ("joint_upper_limits", c.joint_upper), ("joint_lower_limits", c.joint_lower)):
+        if k in policy_dict and not np.allclose(np.asarray(policy_dict[k], np.float64), np.ctypeslib.as_array(arr), rtol=1e-6, atol=1e-7):
+            raise ValueError(f"exported policy's {k} differs from the env's")
+    if policy_dict["in_shape"][1] != c.observation_history * 36:
+        raise ValueError(f"exported policy expects {policy_dict['in_shape'][1]} inputs, the env observes {c.observation_history * 36}")
+
+
+def evaluate_policy(env, policy_dict: Dict, n_envs: int = 8192, episode_length: int = 1000, n_steps: Optional[int] = None, seed: int = 0,
+                    randomization_fn=None, precision: int = 3, unroll_length: int = 20, device=None) -> Dict[str, float]:
+    """Evaluation at scale of a policy in the reference's DEPLOYMENT format (the dict / JSON ``export.convert_params`` writes,
+    reference ``export.py:13-81`` -- what the robot's controller loads): the deterministic policy drives ``n_envs`` envs for
+    ``n_steps`` steps (default: one full episode) on the device, and the completed episodes are summarised like Brax's
+    ``episode_metrics`` (mean episode reward, length, the 18 reward terms, terminations).  SURVEY.md 8(f) N4: the train ->
+    export -> evaluate loop without leaving the GPU.  ``randomization_fn`` as in ``wrappers.wrap``."""
+    from . import parallel, prng, wrappers
+    check_export_against_env(policy_dict, env)
+    if device is None:
+        device = torch.device("cuda", env.device_index())
+    policy = PolicyMLP.from_export(policy_dict, device=device, precision=precision)
+    tenv = wrappers.wrap(env, episode_length=episode_length, randomization_fn=randomization_fn)
+    keys = np.ascontiguousarray(prng.split(prng.PRNGKey(seed), n_envs)).view(np.int32)
+    state = tenv.reset(torch.from_numpy(keys).to(device))
+    n_steps = int(episode_length if n_steps is None else n_steps)
+    col = RolloutCollector(tenv, policy, state, unroll_length)
+    done = 0
+    while done < n_steps:
+        col.collect()
+        done += unroll_length
+    torch.cuda.synchronize(device)
+    report = parallel.episode_report(tenv.episode_totals())
+    report["env_steps"] = float(done * n_envs)
+    return report

@@ -929,3 +929,51 @@ def test_step_host_chunked_pipeline_matches_plain_step():
         np.testing.assert_allclose(rt.episode_field("totals").cpu().numpy(), ref.episode_field("totals").cpu().numpy(), rtol=1e-5)
     with pytest.raises(runtime.PupperError):
         rt.step_host(torch.zeros((n, 11)).pin_memory(), h_out)
+
+
+@pytest.mark.gpu
+def test_exported_policy_evaluates_at_scale():
+    """SURVEY 8(f) N4, the train -> export -> evaluate loop: a Brax-shaped parameter tree (observation normaliser + Gaussian-head
+    MLP) goes through export.convert_params (the reference's deployment JSON, export.py:13-81), through JSON text, and drives
+    the CUDA env: the actions equal tanh(mean head of the ORIGINAL normalised network) evaluated in NumPy float64, the contract
+    check refuses an env built with another action scale, and evaluate_policy reports Brax-style episode metrics."""
+    import json
+    from pupperv3_mjx_b200 import export, rollout
+    env = common.make_env()
+    kw = common.env_kwargs()
+    rs = np.random.RandomState(3)
+    w_in = env.observation_size
+    sizes = [w_in, 64, 32, 24]  # 24 = 12 means + 12 log-stds
+    mean, std = rs.randn(w_in) * 0.1, 0.5 + rs.rand(w_in)
+    net = {f"hidden_{i}": {"kernel": rs.randn(sizes[i], sizes[i + 1]) / np.sqrt(sizes[i]), "bias": 0.1 * rs.randn(sizes[i + 1])} for i in range(3)}
+    exported = export.convert_params(({"mean": mean, "std": std}, {"params": net}), activation="swish", action_scale=kw["action_scale"],
+                                     kp=kw["position_control_kp"], kd=kw["dof_damping"], default_pose=kw["default_pose"],
+                                     joint_upper_limits=kw["joint_upper_limits"], joint_lower_limits=kw["joint_lower_limits"], use_imu=True,
+                                     observation_history=kw["observation_history"], maximum_pitch_command=kw["maximum_pitch_command"],
+                                     maximum_roll_command=kw["maximum_roll_command"])
+    policy_dict = json.loads(json.dumps(exported))  # what the robot's controller would read from disk
+    # the kernel's actions against the original network in float64
+    obs = torch.randn((300, w_in), device="cuda")
+    pol = rollout.PolicyMLP.from_export(policy_dict, device="cuda", precision=3)
+    x = (obs.double().cpu().numpy() - mean) / std
+    for i in range(3):
+        x = x @ net[f"hidden_{i}"]["kernel"] + net[f"hidden_{i}"]["bias"]
+        if i < 2:
+            x = x / (1.0 + np.exp(-x))
+    want = np.tanh(x[:, :12])
+    np.testing.assert_allclose(pol(obs).cpu().numpy(), want, atol=2e-5)
+    # the deployment contract is checked against the env
+    rollout.check_export_against_env(policy_dict, env)
+    with pytest.raises(ValueError, match="action_scale"):
+        rollout.check_export_against_env(policy_dict, common.make_env(action_scale=0.5))
+    with pytest.raises(ValueError, match="observation_history|inputs"):
+        rollout.check_export_against_env(policy_dict, common.make_env(observation_history=3))
+    # evaluation at scale: 2048 envs x 60 steps with 25-step episodes -> every env completes two episodes
+    rep = rollout.evaluate_policy(env, policy_dict, n_envs=2048, episode_length=25, n_steps=60, seed=1)
+    assert rep["episodes"] >= 2 * 2048 and 0 < rep["length"] <= 25 and np.isfinite(rep["sum_reward"]) and rep["env_steps"] == 60 * 2048
+    assert set(abi_metric_names()) <= set(rep)
+
+
+def abi_metric_names():
+    from pupperv3_mjx_b200 import abi
+    return abi.METRIC_NAMES
