@@ -194,6 +194,7 @@ class EnvRuntime:
         self.state.obs = self.obs.data_ptr()
         self.out = abi.PupperStepOut()
         self._out_variants = {}  # (reward ptr, done ptr) -> PupperStepOut with those two outputs redirected (step(reward_out=, done_out=))
+        self._host_fast = {}     # (h_action ptr, h_out ptr) -> prebuilt arguments of the one-launch host path (step_host)
         self.out.reward, self.out.done, self.out.metrics = self.reward.data_ptr(), self.done.data_ptr(), self.metrics.data_ptr()
         self.dbg: Dict[str, torch.Tensor] = {}
         if debug:
@@ -240,6 +241,7 @@ class EnvRuntime:
 
     def set_dr(self, sys_v: Optional[System]):
         """Stage the batched DR leaves (domain_randomize output) on the device as SoA."""
+        self._host_fast = {}  # the prebuilt host-path arguments point at the DR struct
         if sys_v is None or not sys_v.is_batched():
             self._dr_struct, self._dr_tensors = None, {}
             return
@@ -400,6 +402,15 @@ class EnvRuntime:
         ``PUPPER_HOST_OUT_COPY=1``) selects the older path: contiguous env ranges pipelined over three streams (actions in,
         step kernels in order, observations out) with explicit copies."""
         n = self.n_envs
+        if chunks is None and self._host_fast:  # buffers seen before on the one-launch path: everything is validated and prebuilt
+            fast = self._host_fast.get((h_action.data_ptr(), h_out.data_ptr()))
+            if fast is not None and torch.cuda.current_device() == self.device_index:
+                cur = torch.cuda.current_stream(self.device)
+                rc = self.lib.pupper_step(self._model, n, fast[0], fast[1], fast[2], None, fast[3], fast[4], cur.cuda_stream)
+                if rc != 0:
+                    _check(self.lib, rc, "pupper_step")
+                self.launches += 1
+                return cur
         w = self.cfg.observation_history * abi.OBS_DIM
         if h_action.dtype != torch.float32 or h_action.numel() != n * abi.NU or h_out.dtype != torch.float32 or h_out.numel() != n * (w + 2):
             raise PupperError("h_action must be float32 [n_envs, 12] and h_out float32 [n_envs * (H*36 + 2)]")
@@ -413,6 +424,7 @@ class EnvRuntime:
                 raise PupperError(f"{name} must be a contiguous, pinned host tensor (a pageable buffer turns the asynchronous copies "
                                   "synchronous and serialises the three-stream pipeline)")
             ok.add((t.data_ptr(), t.numel()))
+        requested_chunks = chunks
         if chunks is None:
             # zero-copy results (below): one launch at every size -- the CTAs' stores to the pinned buffer are spread over the
             # kernel's run time, which pipelines the PCIe traffic by itself (65,536 envs: 9.25e7 env-steps/s against 8.0e7 for
@@ -464,6 +476,12 @@ class EnvRuntime:
             self.launches += 1
             if not self._zero_copy_out:
                 h_out.view(-1).copy_(self._out_pack, non_blocking=True)
+            elif self._zero_copy_action and requested_chunks is None:
+                if len(self._host_fast) > 64:
+                    self._host_fast.clear()
+                self._host_fast[(h_action.data_ptr(), h_out.data_ptr())] = (
+                    C.byref(self._dr_struct) if self._dr_struct else None, C.byref(self.state), act_ptr, C.byref(out),
+                    C.byref(self.episode) if self.episode else None, h_action, h_out)  # (the tensors are kept alive with their entry)
             return cur
         done_ev = self._done_ev  # re-recorded every call: wait on it before the next call (the policy needs obs anyway)
         ha, flat = h_action.view(n, abi.NU), h_out.view(-1)
