@@ -34,6 +34,10 @@ def key_of(chain):
     for i, (f, l) in enumerate(chain):
         if f == "pupper_kernel.cuh" and i + 1 < len(chain) and chain[i + 1][0] == "pupper_env.cu":
             return (f, l)
+    # env-level code: env_body is inlined into the kernel, so the outermost frame is the kernel's one-line body; take the frame
+    # that sits directly in env_body
+    if len(chain) >= 2 and chain[-1][0] == "pupper_env.cu" and chain[-2][0] == "pupper_env.cu":
+        return chain[-2]
     return chain[-1]
 
 ex, sm, st, sta = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
