@@ -55,3 +55,30 @@ def test_convert_params_folds_normalisation_and_halves_the_head():
     np.testing.assert_allclose(W1, net["hidden_1"]["kernel"][:, :12])
     layers = export.policy_from_dict(d)
     assert [w.shape for w, _, _ in layers] == [(72, 32), (32, 12)] and layers[-1][2] == "tanh"
+
+
+def test_exported_policy_contract_is_checked_against_the_env():
+    """rollout.check_export_against_env (no GPU): the deployment JSON carries the env parameters the policy was trained with
+    (reference export.py:65-79); an env built differently must be refused before the policy drives it."""
+    import json
+    from pupperv3_mjx_b200 import rollout
+    kw = common.env_kwargs()
+    env = common.make_env()
+    w = env.observation_size
+    rs = np.random.RandomState(0)
+    net = {"hidden_0": {"kernel": rs.randn(w, 16), "bias": rs.randn(16)}, "hidden_1": {"kernel": rs.randn(16, 24), "bias": rs.randn(24)}}
+    d = export.convert_params(({"mean": np.zeros(w), "std": np.ones(w)}, {"params": net}), activation="elu", action_scale=kw["action_scale"],
+                              kp=kw["position_control_kp"], kd=kw["dof_damping"], default_pose=kw["default_pose"], joint_upper_limits=kw["joint_upper_limits"],
+                              joint_lower_limits=kw["joint_lower_limits"], use_imu=True, observation_history=kw["observation_history"],
+                              maximum_pitch_command=kw["maximum_pitch_command"], maximum_roll_command=kw["maximum_roll_command"])
+    d = json.loads(json.dumps(d))
+    rollout.check_export_against_env(d, env)  # matches
+    for key, bad_env in (("action_scale", common.make_env(action_scale=0.3)), ("kp", common.make_env(position_control_kp=7.0)),
+                         ("use_imu", common.make_env(use_imu=False))):
+        with pytest.raises(ValueError, match=key):
+            rollout.check_export_against_env(d, bad_env)
+    worse = dict(d, default_joint_pos=[0.0] * 12)
+    with pytest.raises(ValueError, match="default_joint_pos"):
+        rollout.check_export_against_env(worse, env)
+    layers = export.policy_from_dict(d)
+    assert [W.shape for W, _, _ in layers] == [(w, 16), (16, 12)] and layers[-1][2] == "tanh"
